@@ -1,0 +1,691 @@
+// C-ABI entry points + host-side driver of the Lloyd loop (see include/b2kmeans.h for the reference
+// interfaces each one replaces).  The driver enqueues {fused assign+update | generic assign, update} ->
+// fixed-order partial reduce -> NCCL allreduce of one fused f64 buffer -> finalize, several iterations ahead
+// of the host; convergence lives on the device (B2kLoopState) and is polled every `check_every` iterations.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "b2k_internal.cuh"
+
+static std::string g_last_error;  // failures of calls that have no context
+
+int b2k_fail(b2k_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  else g_last_error = msg;
+  return code;
+}
+
+extern "C" int b2k_version(void) { return B2K_VERSION; }
+
+extern "C" const char* b2k_last_error(const b2k_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" int b2k_ctx_create(int device, b2k_ctx** out) {
+  if (!out) return b2k_fail(nullptr, B2K_ERR_INVALID, "b2k_ctx_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return b2k_fail(nullptr, B2K_ERR_CUDA,
+                    std::string("b2k_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                        "); libb2kmeans has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev)
+    return b2k_fail(nullptr, B2K_ERR_INVALID, "b2k_ctx_create: device index out of range");
+  b2k_ctx* ctx = new b2k_ctx();
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    delete ctx;
+    return b2k_fail(nullptr, B2K_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return b2k_fail(nullptr, B2K_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  }
+  if (prop.major != 10) {
+    delete ctx;
+    return b2k_fail(nullptr, B2K_ERR_UNSUPPORTED,
+                    "libb2kmeans is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor));
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaHostAlloc((void**)&ctx->h_state, sizeof(B2kLoopState), cudaHostAllocDefault)) != cudaSuccess) {
+    delete ctx;
+    return b2k_fail(nullptr, B2K_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return B2K_OK;
+}
+
+extern "C" int b2k_ctx_destroy(b2k_ctx* ctx) {
+  if (!ctx) return B2K_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->nccl) b2k_comm_destroy(ctx);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+    if (ctx->dev_stage[i]) cudaFree(ctx->dev_stage[i]);
+    if (ctx->stage_evt[i]) cudaEventDestroy(ctx->stage_evt[i]);
+  }
+  if (ctx->h_state) cudaFreeHost(ctx->h_state);
+  delete ctx;
+  return B2K_OK;
+}
+
+extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_ctx_set_option: NULL argument");
+  std::string k(key);
+  if (k == "kernel_path") {
+    if (value < B2K_PATH_AUTO || value > B2K_PATH_TCGEN05)
+      return b2k_fail(ctx, B2K_ERR_INVALID, "kernel_path must be 0 (auto), 1 (generic) or 2 (tcgen05)");
+    ctx->kernel_path = (int)value;
+  } else if (k == "time_kernels") {
+    ctx->time_kernels = value ? 1 : 0;
+  } else if (k == "check_every") {
+    if (value < 1) return b2k_fail(ctx, B2K_ERR_INVALID, "check_every must be >= 1");
+    ctx->check_every = (int)value;
+  } else if (k == "grid_limit") {
+    if (value < 0) return b2k_fail(ctx, B2K_ERR_INVALID, "grid_limit must be >= 0");
+    ctx->grid_limit = (int)value;
+  } else {
+    return b2k_fail(ctx, B2K_ERR_INVALID, "unknown option: " + k);
+  }
+  return B2K_OK;
+}
+
+extern "C" int b2k_get_stats(const b2k_ctx* ctx, b2k_stats* out) {
+  if (!ctx || !out) return B2K_ERR_INVALID;
+  *out = ctx->stats;
+  return B2K_OK;
+}
+extern "C" int b2k_reset_stats(b2k_ctx* ctx) {
+  if (!ctx) return B2K_ERR_INVALID;
+  ctx->stats = b2k_stats{};
+  return B2K_OK;
+}
+
+int b2k_scratch_reserve(b2k_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return B2K_OK;
+  if (ctx->scratch) {
+    B2K_CUDA_OK(ctx, cudaDeviceSynchronize());
+    B2K_CUDA_OK(ctx, cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  size_t want = bytes + (bytes >> 3) + (1 << 20);
+  cudaError_t e = cudaMalloc(&ctx->scratch, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return b2k_fail(ctx, B2K_ERR_NOMEM, "scratch cudaMalloc of " + std::to_string(want) + " bytes failed: " +
+                                            cudaGetErrorString(e));
+  }
+  ctx->scratch_bytes = want;
+  return B2K_OK;
+}
+
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over ctx->scratch.
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+int check_shape(b2k_ctx* ctx, const char* who, const void* X, int64_t n, int d, int k) {
+  if (!ctx) return b2k_fail(nullptr, B2K_ERR_INVALID, std::string(who) + ": ctx is NULL");
+  if (!X || n < 0 || d <= 0 || k <= 0)
+    return b2k_fail(ctx, B2K_ERR_INVALID, std::string(who) + ": bad X/n/d/k");
+  return B2K_OK;
+}
+
+bool want_fused(b2k_ctx* ctx, int64_t n, int d, int k, const float* X, int* status) {
+  *status = B2K_OK;
+  bool ok = b2k_fused_supported(ctx, n, d, k, X);
+  if (ctx->kernel_path == B2K_PATH_GENERIC) return false;
+  if (ctx->kernel_path == B2K_PATH_TCGEN05 && !ok) {
+    *status = b2k_fail(ctx, B2K_ERR_UNSUPPORTED,
+                       "kernel_path=tcgen05 requested but shape (n=" + std::to_string(n) + ", d=" +
+                           std::to_string(d) + ", k=" + std::to_string(k) +
+                           ") is outside the fused kernel's instantiations");
+    return false;
+  }
+  return ok;
+}
+
+// Scratch footprint of one assign/lloyd call.
+struct LoopBuffers {
+  B2kLoopState* st;
+  double* R;
+  double* shift_scratch;
+  float* cnorm;
+  // generic
+  int32_t* labels;
+  float* partials;
+  int32_t* counts;
+  int P;
+  // fused
+  B2kFusedPlan plan;
+  void* plan_scratch;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Lloyd loop
+// ------------------------------------------------------------------------------------------------
+static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, float* C, int max_iter, double tol,
+                      int* n_iter_out, double* shift_out, cudaStream_t s) {
+  if (max_iter < 0) return b2k_fail(ctx, B2K_ERR_INVALID, "lloyd: max_iter < 0");
+  int st_rc;
+  const bool fused = want_fused(ctx, n, d, k, X, &st_rc);
+  B2K_TRY(st_rc);
+  ctx->stats.last_path = fused ? B2K_PATH_TCGEN05 : B2K_PATH_GENERIC;
+
+  LoopBuffers B{};
+  size_t gen_bytes = 0;
+  if (fused) {
+    B2K_TRY(b2k_fused_plan(ctx, n, d, k, &B.plan));
+  } else {
+    gen_bytes = b2k_update_generic_scratch(ctx, n, d, k, &B.P);
+  }
+  const size_t rlen = b2k_reduced_len(k, d);
+  size_t total = 4096 + align_up(rlen * 8, 256) + align_up((size_t)k * 8, 256) + align_up((size_t)k * 4, 256) +
+                 (fused ? align_up(B.plan.scratch_bytes, 1024) + 1024
+                        : align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 1024);
+  B2K_TRY(b2k_scratch_reserve(ctx, total));
+  Arena A(ctx->scratch);
+  B.st = A.take<B2kLoopState>(1);
+  B.R = A.take<double>(rlen);
+  B.shift_scratch = A.take<double>(k);
+  B.cnorm = A.take<float>(k);
+  if (fused) {
+    A.off = align_up(A.off, 1024);
+    B.plan_scratch = A.base + A.off;
+  } else {
+    B.labels = A.take<int32_t>(n > 0 ? n : 1);
+    B.partials = A.take<float>((size_t)B.P * k * d);
+    B.counts = A.take<int32_t>((size_t)B.P * k);
+  }
+
+  B2kLoopState init{};
+  init.iter = 0;
+  init.done = max_iter == 0 ? 1 : 0;
+  init.max_iter = max_iter;
+  init.blocks_done = 0;
+  init.tol = tol;
+  init.shift = 0.0;
+  init.cost = 0.0;
+  *ctx->h_state = init;
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(B.st, ctx->h_state, sizeof(B2kLoopState), cudaMemcpyHostToDevice, s));
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));  // h_state is reused as the D2H mirror below
+
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t loop0 = nullptr, loop1 = nullptr;
+  if (ctx->time_kernels) {
+    B2K_CUDA_OK(ctx, cudaEventCreate(&loop0));
+    B2K_CUDA_OK(ctx, cudaEventCreate(&loop1));
+    B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
+  }
+
+  int launched = 0;
+  bool done = (max_iter == 0);
+  while (!done && launched < max_iter) {
+    int burst = std::min(ctx->check_every, max_iter - launched);
+    for (int b = 0; b < burst; ++b) {
+      if (fused) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->time_kernels) {
+          B2K_CUDA_OK(ctx, cudaEventCreate(&e0));
+          B2K_CUDA_OK(ctx, cudaEventCreate(&e1));
+          ev.push_back(e0);
+          ev.push_back(e1);
+          B2K_CUDA_OK(ctx, cudaEventRecord(e0, s));
+        }
+        B2K_TRY(b2k_launch_fused(ctx, B.plan, B.plan_scratch, X, n, d, C, k, nullptr, nullptr, true, B.st, s));
+        if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(e1, s));
+        float* partials;
+        int32_t* counts;
+        double* cost_partials;
+        b2k_fused_views(B.plan, B.plan_scratch, k, d, &partials, &counts, &cost_partials);
+        B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.grid, k, d, B.R, B.st, s));
+      } else {
+        B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
+        B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, B.cnorm, k, B.labels, nullptr, B.st, s));
+        B2K_TRY(b2k_launch_update_generic(ctx, X, n, d, B.labels, k, B.P, B.partials, B.counts, B.st, s));
+        B2K_TRY(b2k_launch_reduce_partials(ctx, B.partials, B.counts, nullptr, B.P, k, d, B.R, B.st, s));
+      }
+      if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, B.R, rlen, s));
+      B2K_TRY(b2k_launch_finalize(ctx, B.R, C, k, d, B.shift_scratch, B.st, s));
+      ++launched;
+    }
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_state, B.st, sizeof(B2kLoopState), cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    done = ctx->h_state->done != 0;
+  }
+  if (max_iter == 0) {
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  }
+  if (ctx->time_kernels) {
+    B2K_CUDA_OK(ctx, cudaEventRecord(loop1, s));
+    B2K_CUDA_OK(ctx, cudaEventSynchronize(loop1));
+    float ms = 0.f;
+    B2K_CUDA_OK(ctx, cudaEventElapsedTime(&ms, loop0, loop1));
+    ctx->stats.last_loop_ms = ms;
+    double acc = 0.0;
+    int cnt = 0;
+    int iters_done = ctx->h_state->iter;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+      float m = 0.f;
+      cudaEventElapsedTime(&m, ev[i], ev[i + 1]);
+      if ((int)(i / 2) < iters_done) { acc += m; ++cnt; }  // launches after convergence are no-ops
+      cudaEventDestroy(ev[i]);
+      cudaEventDestroy(ev[i + 1]);
+    }
+    ctx->stats.last_fused_ms = cnt ? acc / cnt : 0.0;
+    cudaEventDestroy(loop0);
+    cudaEventDestroy(loop1);
+  }
+  ctx->stats.last_n_iter = ctx->h_state->iter;
+  if (n_iter_out) *n_iter_out = ctx->h_state->iter;
+  if (shift_out) *shift_out = ctx->h_state->shift;
+  return B2K_OK;
+}
+
+extern "C" int b2k_kmeans_lloyd(b2k_ctx* ctx, const float* X, int64_t n_local, int d, int k, float* centers,
+                                int max_iter, double tol, int* n_iter_out, double* shift_out, uintptr_t stream) {
+  B2K_TRY(check_shape(ctx, "b2k_kmeans_lloyd", X, n_local, d, k));
+  if (!centers) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_lloyd: centers is NULL");
+  B2K_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return lloyd_impl(ctx, X, n_local, d, k, centers, max_iter, tol, n_iter_out, shift_out,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// assign (+ optional total cost): labels/mindist may be NULL.  Scratch beyond `scratch_off` is used.
+// ------------------------------------------------------------------------------------------------
+static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                       float* mindist, double* cost_dev /* device, 1 double, may be NULL */, size_t scratch_off,
+                       cudaStream_t s) {
+  int st_rc;
+  const bool fused = want_fused(ctx, n, d, k, X, &st_rc);
+  B2K_TRY(st_rc);
+  ctx->stats.last_path = fused ? B2K_PATH_TCGEN05 : B2K_PATH_GENERIC;
+  if (fused) {
+    B2kFusedPlan plan;
+    B2K_TRY(b2k_fused_plan(ctx, n, d, k, &plan));
+    size_t need = align_up(scratch_off, 1024) + align_up(plan.scratch_bytes, 1024) + 1024;
+    if (need > ctx->scratch_bytes && scratch_off != 0)
+      return b2k_fail(ctx, B2K_ERR_STATE, "assign_impl: scratch must be pre-reserved by the caller");
+    B2K_TRY(b2k_scratch_reserve(ctx, need));
+    void* ps = static_cast<char*>(ctx->scratch) + align_up(scratch_off, 1024);
+    B2K_TRY(b2k_launch_fused(ctx, plan, ps, X, n, d, C, k, labels, mindist, false, nullptr, s));
+    if (cost_dev) {
+      float* partials;
+      int32_t* counts;
+      double* cost_partials;
+      b2k_fused_views(plan, ps, k, d, &partials, &counts, &cost_partials);
+      // fold the per-CTA cost partials in index order
+      B2K_TRY(b2k_launch_fold_f64(ctx, cost_partials, plan.grid, cost_dev, s));
+    }
+  } else {
+    const int nblocks = 1024;
+    size_t need = align_up(scratch_off, 256) + align_up((size_t)k * 4, 256) +
+                  (cost_dev && !mindist ? align_up((size_t)(n > 0 ? n : 1) * 4, 256) : 0) +
+                  align_up((size_t)nblocks * 8, 256) + 1024;
+    if (need > ctx->scratch_bytes && scratch_off != 0)
+      return b2k_fail(ctx, B2K_ERR_STATE, "assign_impl: scratch must be pre-reserved by the caller");
+    B2K_TRY(b2k_scratch_reserve(ctx, need));
+    Arena A(ctx->scratch);
+    A.off = scratch_off;
+    float* cnorm = A.take<float>(k);
+    float* md = mindist;
+    if (cost_dev && !md) md = A.take<float>(n > 0 ? n : 1);
+    double* blocks = A.take<double>(nblocks);
+    B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, cnorm, nullptr, s));
+    B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, cnorm, k, labels, md, nullptr, s));
+    if (cost_dev) B2K_TRY(b2k_launch_sum_f32_to_f64(ctx, md, n, cost_dev, blocks, nblocks, s));
+  }
+  return B2K_OK;
+}
+
+// upper bound of what assign_impl needs past scratch_off
+static size_t assign_scratch_bound(b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
+  size_t b = align_up((size_t)k * 4, 256) + align_up((size_t)(n > 0 ? n : 1) * 4, 256) + 1024 * 8 + 4096;
+  if (b2k_fused_supported(ctx, n, d, k, X) && ctx->kernel_path != B2K_PATH_GENERIC) {
+    B2kFusedPlan plan;
+    if (b2k_fused_plan(ctx, n, d, k, &plan) == B2K_OK) b = std::max(b, align_up(plan.scratch_bytes, 1024) + 4096);
+  }
+  return b;
+}
+
+extern "C" int b2k_kmeans_assign(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* centers, int k,
+                                 int32_t* labels_out, float* mindist_out, uintptr_t stream) {
+  B2K_TRY(check_shape(ctx, "b2k_kmeans_assign", X, n, d, k));
+  if (!centers) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_assign: centers is NULL");
+  if (n == 0) return B2K_OK;
+  B2K_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return assign_impl(ctx, X, n, d, centers, k, labels_out, mindist_out, nullptr, 0,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialisers
+// ------------------------------------------------------------------------------------------------
+namespace {
+// global row bookkeeping across ranks
+struct Rows {
+  std::vector<int64_t> sizes;  // per rank
+  int64_t offset = 0;          // this rank's first global row
+  int64_t total = 0;
+};
+
+int gather_sizes(b2k_ctx* ctx, int64_t n_local, Rows* rows, cudaStream_t s) {
+  rows->sizes.assign(ctx->nranks, 0);
+  if (ctx->nranks == 1) {
+    rows->sizes[0] = n_local;
+  } else {
+    B2K_TRY(b2k_scratch_reserve(ctx, 4096 + 16 * (size_t)ctx->nranks));
+    int64_t* send = reinterpret_cast<int64_t*>(ctx->scratch);
+    int64_t* recv = send + 32;
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(send, &n_local, 8, cudaMemcpyHostToDevice, s));
+    B2K_TRY(b2k_comm_allgather_i64(ctx, send, recv, 1, s));
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(rows->sizes.data(), recv, 8 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  }
+  rows->offset = 0;
+  rows->total = 0;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r < ctx->rank) rows->offset += rows->sizes[r];
+    rows->total += rows->sizes[r];
+  }
+  return B2K_OK;
+}
+
+// out[m,d] (device) <- rows with the given sorted GLOBAL indices, identical on every rank.
+int fetch_global_rows(b2k_ctx* ctx, const float* X, int64_t n_local, int d, const Rows& rows,
+                      const std::vector<int64_t>& gidx, float* out, int64_t* idx_dev, cudaStream_t s) {
+  const int m = (int)gidx.size();
+  if (m == 0) return B2K_OK;
+  B2K_CUDA_OK(ctx, cudaMemsetAsync(out, 0, (size_t)m * d * sizeof(float), s));
+  // contiguous run of indices owned by this rank (gidx is sorted)
+  int lo = 0;
+  while (lo < m && gidx[lo] < rows.offset) ++lo;
+  int hi = lo;
+  while (hi < m && gidx[hi] < rows.offset + n_local) ++hi;
+  if (hi > lo) {
+    std::vector<int64_t> local(hi - lo);
+    for (int i = lo; i < hi; ++i) local[i - lo] = gidx[i] - rows.offset;
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(idx_dev, local.data(), local.size() * 8, cudaMemcpyHostToDevice, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `local` dies at scope end
+    B2K_TRY(b2k_launch_gather_rows(ctx, X, d, idx_dev, hi - lo, out, lo, s));
+  }
+  if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f32(ctx, out, (size_t)m * d, s));
+  return B2K_OK;
+}
+
+std::vector<int64_t> sample_distinct(std::mt19937_64& rng, int64_t total, int m) {
+  // Floyd's algorithm: m distinct values in [0,total)
+  std::vector<int64_t> chosen;
+  chosen.reserve(m);
+  for (int64_t j = total - m; j < total; ++j) {
+    std::uniform_int_distribution<int64_t> U(0, j);
+    int64_t t = U(rng);
+    if (std::find(chosen.begin(), chosen.end(), t) == chosen.end()) chosen.push_back(t);
+    else chosen.push_back(j);
+  }
+  std::sort(chosen.begin(), chosen.end());
+  return chosen;
+}
+
+// Weighted greedy k-means++ followed by a few weighted Lloyd steps on the (small) candidate set — host side.
+void reduce_candidates(const std::vector<float>& P, const std::vector<double>& wts, int M, int d, int k,
+                       std::mt19937_64& rng, std::vector<float>* out) {
+  std::vector<double> C((size_t)k * d), d2(M), nd2(M), bestd2(M);
+  auto sq = [&](int a, const double* c) {
+    double s = 0;
+    const float* p = &P[(size_t)a * d];
+    for (int t = 0; t < d; ++t) { double df = (double)p[t] - c[t]; s += df * df; }
+    return s;
+  };
+  auto pick = [&](const std::vector<double>& prob, double tot) {
+    std::uniform_real_distribution<double> U(0.0, tot);
+    double u = U(rng), acc = 0;
+    for (int i = 0; i < M; ++i) { acc += prob[i]; if (u < acc) return i; }
+    return M - 1;
+  };
+  std::vector<double> prob(M);
+  double tot = 0;
+  for (int i = 0; i < M; ++i) { prob[i] = wts[i]; tot += prob[i]; }
+  int first = pick(prob, tot);
+  for (int t = 0; t < d; ++t) C[t] = P[(size_t)first * d + t];
+  for (int i = 0; i < M; ++i) d2[i] = sq(i, &C[0]);
+  const int trials = 2 + (int)std::log((double)std::max(k, 2));
+  std::vector<double> cand(d);
+  for (int j = 1; j < k; ++j) {
+    tot = 0;
+    for (int i = 0; i < M; ++i) { prob[i] = wts[i] * d2[i]; tot += prob[i]; }
+    double best_pot = -1;
+    int best_c = 0;
+    for (int tr = 0; tr < trials; ++tr) {
+      int c = tot > 0 ? pick(prob, tot) : (int)(rng() % M);
+      for (int t = 0; t < d; ++t) cand[t] = P[(size_t)c * d + t];
+      double pot = 0;
+      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], sq(i, cand.data())); pot += wts[i] * nd2[i]; }
+      if (best_pot < 0 || pot < best_pot) { best_pot = pot; best_c = c; bestd2 = nd2; }
+    }
+    for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = P[(size_t)best_c * d + t];
+    d2 = bestd2;
+  }
+  std::vector<int> lab(M);
+  for (int it = 0; it < 10; ++it) {
+    for (int i = 0; i < M; ++i) {
+      double b = 1e300;
+      int bj = 0;
+      for (int j = 0; j < k; ++j) { double s = sq(i, &C[(size_t)j * d]); if (s < b) { b = s; bj = j; } }
+      lab[i] = bj;
+    }
+    std::vector<double> S((size_t)k * d, 0.0), W(k, 0.0);
+    for (int i = 0; i < M; ++i) {
+      W[lab[i]] += wts[i];
+      for (int t = 0; t < d; ++t) S[(size_t)lab[i] * d + t] += wts[i] * (double)P[(size_t)i * d + t];
+    }
+    for (int j = 0; j < k; ++j)
+      if (W[j] > 0)
+        for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = S[(size_t)j * d + t] / W[j];
+  }
+  out->resize((size_t)k * d);
+  for (size_t e = 0; e < (size_t)k * d; ++e) (*out)[e] = (float)C[e];
+}
+}  // namespace
+
+static int init_random(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, uint64_t seed, float* C,
+                       cudaStream_t s) {
+  Rows rows;
+  B2K_TRY(gather_sizes(ctx, n, &rows, s));
+  if (rows.total < k)
+    return b2k_fail(ctx, B2K_ERR_INVALID, "init=random: fewer rows (" + std::to_string(rows.total) + ") than k");
+  std::mt19937_64 rng(seed);
+  std::vector<int64_t> gidx = sample_distinct(rng, rows.total, k);
+  B2K_TRY(b2k_scratch_reserve(ctx, 4096 + (size_t)k * 8));
+  int64_t* idx_dev = reinterpret_cast<int64_t*>(static_cast<char*>(ctx->scratch) + 1024);
+  return fetch_global_rows(ctx, X, n, d, rows, gidx, C, idx_dev, s);
+}
+
+// Scalable k-means++ (k-means||): the reference forwards init="scalable-k-means++", oversampling_factor=2.0
+// (clustering.py:134-136).  Distributional parity only (the reference's own seeded test is xfail).
+static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, uint64_t seed,
+                                double oversampling, float* C, cudaStream_t s) {
+  const int rounds = 5;
+  Rows rows;
+  B2K_TRY(gather_sizes(ctx, n, &rows, s));
+  if (rows.total < k)
+    return b2k_fail(ctx, B2K_ERR_INVALID, "init=k-means||: fewer rows (" + std::to_string(rows.total) + ") than k");
+  const double ell = oversampling * k;
+  const int cap = (int)std::min<int64_t>(rows.total, (int64_t)(4 * ell) + 64);  // per-round candidate cap
+  const int Mmax = 1 + rounds * cap + k;
+  // scratch: [0,64K) control | mind[n] | dn[n] | labels[n] | cand[Mmax*d] | newc[cap*d] | hist[Mmax] | assign scratch
+  size_t nn = (size_t)(n > 0 ? n : 1);
+  size_t fixed = 65536 + 3 * align_up(nn * 4, 256) + align_up((size_t)Mmax * d * 4, 256) +
+                 align_up((size_t)cap * d * 4, 256) + align_up((size_t)Mmax * 8, 256) + 4096;
+  size_t abound = std::max(assign_scratch_bound(ctx, n, d, Mmax, X), assign_scratch_bound(ctx, n, d, cap, X));
+  B2K_TRY(b2k_scratch_reserve(ctx, fixed + abound + 4096));
+  Arena A(ctx->scratch);
+  int64_t* idx_dev = A.take<int64_t>(cap + 8);
+  int* n_picked_dev = A.take<int>(8);
+  double* phi_dev = A.take<double>(4);
+  A.off = 65536;
+  float* mind = A.take<float>(nn);
+  float* dn = A.take<float>(nn);
+  int32_t* labels = A.take<int32_t>(nn);
+  float* cand = A.take<float>((size_t)Mmax * d);
+  float* newc = A.take<float>((size_t)cap * d);
+  double* hist = A.take<double>(Mmax);
+  const size_t assign_off = align_up(A.off, 1024);
+
+  std::mt19937_64 rng(seed);
+  int M = 0;
+  {  // first candidate: one uniformly random row
+    std::uniform_int_distribution<int64_t> U(0, rows.total - 1);
+    std::vector<int64_t> g{U(rng)};
+    B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, g, cand, idx_dev, s));
+    M = 1;
+    B2K_TRY(assign_impl(ctx, X, n, d, cand, 1, nullptr, mind, phi_dev, assign_off, s));
+  }
+  std::vector<int64_t> picked_host(cap);
+  std::vector<int64_t> counts_host(ctx->nranks);
+  for (int r = 0; r < rounds; ++r) {
+    double phi = 0;
+    if (r > 0) {
+      // phi = sum(mind) (deterministic two-level sum)
+      double* blocks = reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + 32768);
+      B2K_TRY(b2k_launch_sum_f32_to_f64(ctx, mind, n, phi_dev, blocks, 1024, s));
+    }
+    if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, phi_dev, 1, s));
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(&phi, phi_dev, 8, cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    if (!(phi > 0)) break;
+    B2K_CUDA_OK(ctx, cudaMemsetAsync(n_picked_dev, 0, sizeof(int), s));
+    B2K_TRY(b2k_launch_bernoulli_pick(ctx, mind, n, rows.offset, ell / phi, seed, r, idx_dev, n_picked_dev, cap, s));
+    int np = 0;
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(&np, n_picked_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    np = std::min(np, cap);
+    if (np > 0) B2K_CUDA_OK(ctx, cudaMemcpy(picked_host.data(), idx_dev, (size_t)np * 8, cudaMemcpyDeviceToHost));
+    std::sort(picked_host.begin(), picked_host.begin() + np);
+    // exchange: every rank learns every rank's picks (global indices), capped in total
+    std::vector<int64_t> all;
+    if (ctx->nranks == 1) {
+      all.assign(picked_host.begin(), picked_host.begin() + np);
+    } else {
+      // fixed-size allgather of [count | cap indices] per rank
+      size_t per = (size_t)cap + 1;
+      size_t need = 65536 + 0;  // control region is large enough? use the newc region temporarily
+      (void)need;
+      int64_t* send = reinterpret_cast<int64_t*>(dn);  // dn is free between rounds
+      if ((size_t)nn * 4 < (per * (ctx->nranks + 1)) * 8)
+        return b2k_fail(ctx, B2K_ERR_UNSUPPORTED, "k-means||: partition too small for the candidate exchange");
+      int64_t* recv = send + per;
+      std::vector<int64_t> pack(per, 0);
+      pack[0] = np;
+      std::copy(picked_host.begin(), picked_host.begin() + np, pack.begin() + 1);
+      B2K_CUDA_OK(ctx, cudaMemcpyAsync(send, pack.data(), per * 8, cudaMemcpyHostToDevice, s));
+      B2K_TRY(b2k_comm_allgather_i64(ctx, send, recv, per, s));
+      std::vector<int64_t> got(per * ctx->nranks);
+      B2K_CUDA_OK(ctx, cudaMemcpyAsync(got.data(), recv, got.size() * 8, cudaMemcpyDeviceToHost, s));
+      B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+      for (int q = 0; q < ctx->nranks; ++q) {
+        int64_t c = got[q * per];
+        for (int64_t i = 0; i < c; ++i) all.push_back(got[q * per + 1 + i]);
+      }
+      std::sort(all.begin(), all.end());
+    }
+    if ((int)all.size() > cap) all.resize(cap);
+    if (all.empty()) continue;
+    const int m = (int)all.size();
+    B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, all, newc, idx_dev, s));
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(cand + (size_t)M * d, newc, (size_t)m * d * 4, cudaMemcpyDeviceToDevice, s));
+    M += m;
+    B2K_TRY(assign_impl(ctx, X, n, d, newc, m, nullptr, dn, nullptr, assign_off, s));
+    B2K_TRY(b2k_launch_min_inplace(ctx, mind, dn, n, s));
+  }
+  if (M < k) {  // top up with distinct random rows so that M >= k
+    std::vector<int64_t> extra = sample_distinct(rng, rows.total, k - M + 1);
+    B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, extra, cand + (size_t)M * d, idx_dev, s));
+    M += (int)extra.size();
+  }
+  // weights = #points closest to each candidate
+  B2K_TRY(assign_impl(ctx, X, n, d, cand, M, labels, nullptr, nullptr, assign_off, s));
+  B2K_TRY(b2k_launch_histogram(ctx, labels, n, M, hist, s));
+  if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, hist, M, s));
+  std::vector<float> P((size_t)M * d);
+  std::vector<double> wts(M);
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(P.data(), cand, P.size() * 4, cudaMemcpyDeviceToHost, s));
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(wts.data(), hist, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  for (auto& w : wts) w = std::max(w, 1e-12);
+  std::vector<float> Ck;
+  reduce_candidates(P, wts, M, d, k, rng, &Ck);  // same seed + same inputs => identical on every rank
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(C, Ck.data(), Ck.size() * 4, cudaMemcpyHostToDevice, s));
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  return B2K_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fit
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2k_kmeans_fit(b2k_ctx* ctx, const float* X, int64_t n_local, int d, int k, int init_mode,
+                              const float* init_centers, int max_iter, double tol, uint64_t seed,
+                              double oversampling, int n_init, float* centers_out, int* n_iter_out,
+                              double* inertia_out, uintptr_t stream) {
+  B2K_TRY(check_shape(ctx, "b2k_kmeans_fit", X, n_local, d, k));
+  if (!centers_out) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: centers_out is NULL");
+  if (n_init != 1)
+    return b2k_fail(ctx, B2K_ERR_UNSUPPORTED, "b2k_kmeans_fit: n_init must be 1 (the reference forces n_init=1)");
+  if (n_local == 0)
+    // reference: core.py:959-962 "A python worker received no data"
+    return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: empty partition (n_local == 0)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  B2K_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  switch (init_mode) {
+    case B2K_INIT_ARRAY:
+      if (!init_centers) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: init_centers is NULL");
+      if (init_centers != centers_out)
+        B2K_CUDA_OK(ctx, cudaMemcpyAsync(centers_out, init_centers, (size_t)k * d * 4, cudaMemcpyDeviceToDevice, s));
+      break;
+    case B2K_INIT_RANDOM:
+      B2K_TRY(init_random(ctx, X, n_local, d, k, seed, centers_out, s));
+      break;
+    case B2K_INIT_KMEANS_PARALLEL:
+      B2K_TRY(init_kmeans_parallel(ctx, X, n_local, d, k, seed, oversampling > 0 ? oversampling : 2.0,
+                                   centers_out, s));
+      break;
+    default:
+      return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: unknown init_mode");
+  }
+  B2K_TRY(lloyd_impl(ctx, X, n_local, d, k, centers_out, max_iter, tol, n_iter_out, nullptr, s));
+  if (inertia_out) {
+    B2K_TRY(b2k_scratch_reserve(ctx, 4096 + assign_scratch_bound(ctx, n_local, d, k, X)));
+    double* cost_dev = reinterpret_cast<double*>(ctx->scratch);
+    B2K_TRY(assign_impl(ctx, X, n_local, d, centers_out, k, nullptr, nullptr, cost_dev, 1024, s));
+    if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, cost_dev, 1, s));
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(inertia_out, cost_dev, 8, cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  }
+  return B2K_OK;
+}

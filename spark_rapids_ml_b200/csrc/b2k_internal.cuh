@@ -1,0 +1,144 @@
+// Internal declarations shared by the translation units of libb2kmeans.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b2kmeans.h"
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident loop state: lets the host enqueue several Lloyd iterations without a D2H sync —
+// every hot-loop kernel returns immediately once `done` is set.
+// ------------------------------------------------------------------------------------------------
+struct B2kLoopState {
+  int iter;                  // completed iterations
+  int done;                  // 1 once shift < tol (or iter == max_iter)
+  int max_iter;
+  unsigned int blocks_done;  // last-block-done counter of the finalize kernel
+  double tol;
+  double shift;              // last sum_j ||dc_j||^2
+  double cost;               // last sum_i min_j ||x_i - c_j||^2 (w.r.t. the centers of that pass)
+};
+
+// Layout of the reduced buffer R (doubles) that crosses NCCL: [k*d sums | k counts | 1 cost].
+static inline size_t b2k_reduced_len(int k, int d) { return (size_t)k * d + k + 1; }
+
+struct B2kNccl;  // opaque (b2k_comm.cu)
+
+struct b2k_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  std::string err;
+  // options
+  int kernel_path = B2K_PATH_AUTO;
+  int time_kernels = 0;
+  int check_every = 4;
+  int grid_limit = 0;
+  // comm
+  B2kNccl* nccl = nullptr;
+  int nranks = 1;
+  int rank = 0;
+  // scratch (device), grown on demand
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // pinned staging for ingest (host) + device staging
+  void* pinned[2] = {nullptr, nullptr};
+  size_t pinned_bytes = 0;
+  void* dev_stage[2] = {nullptr, nullptr};
+  size_t dev_stage_bytes = 0;
+  cudaEvent_t stage_evt[2] = {nullptr, nullptr};
+  int stage_next = 0;
+  // pinned host mirror of the loop state (convergence polls)
+  B2kLoopState* h_state = nullptr;
+  // TMA descriptor encoder (driver entry point, resolved lazily)
+  void* encode_tiled = nullptr;
+  b2k_stats stats{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// error helpers
+// ------------------------------------------------------------------------------------------------
+int b2k_fail(b2k_ctx* ctx, int code, const std::string& msg);
+#define B2K_CUDA_OK(ctx, expr)                                                             \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return b2k_fail((ctx), B2K_ERR_CUDA,                                                 \
+                      std::string(#expr) + ": " + cudaGetErrorName(_e) + ": " +            \
+                          cudaGetErrorString(_e));                                         \
+  } while (0)
+#define B2K_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != B2K_OK) return _s; \
+  } while (0)
+
+int b2k_scratch_reserve(b2k_ctx* ctx, size_t bytes);
+
+// ------------------------------------------------------------------------------------------------
+// generic (any k, d) kernels — b2k_generic.cu
+// ------------------------------------------------------------------------------------------------
+// cnorm[j] = ||c_j||^2 (fp32 from a double accumulation)
+int b2k_launch_center_norms(b2k_ctx* ctx, const float* C, int k, int d, float* cnorm,
+                            const B2kLoopState* st, cudaStream_t s);
+// labels/mindist (either may be NULL) + optional per-CTA cost partials
+int b2k_launch_assign_generic(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C,
+                              const float* cnorm, int k, int32_t* labels, float* mindist,
+                              const B2kLoopState* st, cudaStream_t s);
+// per-cluster partial sums from labels: partials [P][k*d] f32, counts [P][k] i32; returns P via *P_out.
+size_t b2k_update_generic_scratch(b2k_ctx* ctx, int64_t n, int d, int k, int* P_out);
+int b2k_launch_update_generic(b2k_ctx* ctx, const float* X, int64_t n, int d, const int32_t* labels, int k,
+                              int P, float* partials, int32_t* counts, const B2kLoopState* st,
+                              cudaStream_t s);
+// R[k*d+k+1] (double) = fixed-order sum over P partials (+ cost from mindist partial sums)
+int b2k_launch_reduce_partials(b2k_ctx* ctx, const float* partials, const int32_t* counts,
+                               const double* cost_partials, int P, int k, int d, double* R,
+                               const B2kLoopState* st, cudaStream_t s);
+// C <- R.S / R.w (w == 0 keeps C), shift, iter++, done.  shift_scratch: k doubles.
+int b2k_launch_finalize(b2k_ctx* ctx, const double* R, float* C, int k, int d, double* shift_scratch,
+                        B2kLoopState* st, cudaStream_t s);
+// cost partials: sum of mindist over fixed-size row blocks (deterministic two-level)
+int b2k_launch_sum_f32_to_f64(b2k_ctx* ctx, const float* v, int64_t n, double* out /*1*/,
+                              double* block_scratch, int nblocks, cudaStream_t s);
+int b2k_launch_fold_f64(b2k_ctx* ctx, const double* in, int m, double* out /*1*/, cudaStream_t s);
+int b2k_launch_gather_rows(b2k_ctx* ctx, const float* X, int d, const int64_t* rows_local, int m,
+                           float* out, int64_t out_row0, cudaStream_t s);
+// k-means|| helpers
+int b2k_launch_min_inplace(b2k_ctx* ctx, float* a, const float* b, int64_t n, cudaStream_t s);
+int b2k_launch_bernoulli_pick(b2k_ctx* ctx, const float* mind, int64_t n, int64_t row_offset,
+                              double scale /* l/phi */, uint64_t seed, int round, int64_t* picked,
+                              int* n_picked, int cap, cudaStream_t s);
+int b2k_launch_histogram(b2k_ctx* ctx, const int32_t* labels, int64_t n, int m, double* hist,
+                         cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 fused kernel — b2k_fused_tc.cu
+// ------------------------------------------------------------------------------------------------
+struct B2kFusedPlan {
+  int KP = 0, DP = 0;        // padded cluster count / dimension of the instantiation, 0 = unsupported
+  int grid = 0;              // persistent CTAs
+  size_t scratch_bytes = 0;  // Chi/Clo/cnorm + partials/counts/cost
+};
+bool b2k_fused_supported(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X);
+int b2k_fused_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan);
+// One fused pass: (labels_out, mindist_out optional) + partial sums/counts/cost into plan scratch.
+// `do_update` = accumulate partial sums (Lloyd iteration) or labels only (assign/inertia pass).
+int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X,
+                     int64_t n, int d, const float* C, int k, int32_t* labels_out, float* mindist_out,
+                     bool do_update, const B2kLoopState* st, cudaStream_t s);
+// Views into the plan scratch after a fused pass (to feed b2k_launch_reduce_partials)
+void b2k_fused_views(const B2kFusedPlan& plan, void* plan_scratch, int k, int d, float** partials,
+                     int32_t** counts, double** cost_partials);
+
+// ------------------------------------------------------------------------------------------------
+// comm — b2k_comm.cu
+// ------------------------------------------------------------------------------------------------
+int b2k_comm_allreduce_f64(b2k_ctx* ctx, double* buf, size_t count, cudaStream_t s);
+int b2k_comm_allgather_i64(b2k_ctx* ctx, const int64_t* send_dev, int64_t* recv_dev, size_t count_per_rank,
+                           cudaStream_t s);
+int b2k_comm_allreduce_f32(b2k_ctx* ctx, float* buf, size_t count, cudaStream_t s);
+
+// ingest — b2k_ingest.cu (entry point is the C ABI itself)
