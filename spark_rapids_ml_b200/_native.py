@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "b2k_ctx_destroy",
     "b2k_ctx_set_option",
     "b2k_get_stats",
+    "b2k_get_fused_profile",
     "b2k_reset_stats",
     "b2k_comm_unique_id",
     "b2k_comm_init",
@@ -105,6 +106,7 @@ def load_library() -> ctypes.CDLL:
     L.b2k_ctx_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     L.b2k_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.b2k_reset_stats.argtypes = [vp]
+    L.b2k_get_fused_profile.argtypes = [vp, vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.b2k_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.b2k_comm_init.argtypes = [vp, i32, i32, ctypes.c_char_p]
     L.b2k_comm_destroy.argtypes = [vp]
@@ -187,6 +189,13 @@ class Context:
         st = Stats()
         self._check(self._L.b2k_get_stats(self._h, ctypes.byref(st)))
         return {f: getattr(st, f) for f, _ in Stats._fields_}
+
+    def fused_profile(self) -> "np.ndarray":
+        """[grid, warps, 8] int64 cycle counters of the last fused launch (needs option profile_fused=1)."""
+        buf = np.zeros(1024 * 18 * 8, dtype=np.int64)
+        g, w = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self._L.b2k_get_fused_profile(self._h, buf.ctypes.data, buf.size, ctypes.byref(g), ctypes.byref(w)))
+        return buf[: g.value * w.value * 8].reshape(g.value, w.value, 8)
 
     def reset_stats(self) -> None:
         self._check(self._L.b2k_reset_stats(self._h))

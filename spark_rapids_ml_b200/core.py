@@ -1,0 +1,432 @@
+"""Driver- and executor-side fit/transform scaffolding for the KMeans path.
+
+Mirrors the reference's contract (python/src/spark_rapids_ml/core.py):
+  * _CumlCaller._pre_process_data      core.py:463-562   select/cast feature columns, infer dimension
+  * _CumlCaller._call_cuml_fit_func    core.py:742-1013  repartition(num_workers), build the pickled
+                                                         `_train_udf`, run it as ONE BARRIER TASK PER GPU
+                                                         through mapInPandas
+  * _train_udf                         core.py:845-1003  BarrierTaskContext, GPU select, ingest, CumlContext
+                                                         (NCCL uid over allGather), call
+                                                         cuml_fit_func(inputs, params), barrier, partition 0
+                                                         yields the model rows
+  * _CumlEstimator._fit_internal       core.py:1230-1281 collect rows, merge chunks, build the model
+  * _CumlModel(WithColumns)._transform core.py:1797-1941 per-batch predict appended as predictionCol
+  * persistence                        core.py:268-355   metadata JSON + model-attribute JSON under path/data
+
+What is re-designed (B200-first): the executor never stacks Python objects or concatenates on the host —
+each Arrow batch goes host -> pinned -> HBM once through b2k_ingest_append into a device-resident matrix
+(utils.DeviceRowAppender), and `inputs` handed to the fit function are device tensors.  The internal hook keeps
+the reference's signature: cuml_fit_func(inputs: List[Tuple[X, None, None]], params: Dict) -> Dict[str, list].
+"""
+from __future__ import annotations
+
+import json
+import os
+import uuid
+from abc import abstractmethod
+from collections import namedtuple
+from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+
+from .params import _CumlParams
+from .sparkshim import BarrierTaskContext, LocalDataFrame, Params, Row, get_session
+from .utils import DeviceRowAppender, arrow_list_column_buffers, get_logger
+
+# same tags as the reference (core.py:128-175) so the worker-side column contract is recognisable
+Alias = namedtuple("Alias", ("featureVectorType", "featureVectorSize", "featureVectorIndices", "data", "label",
+                             "row_number"))
+col_name_unique_tag = "c3BhcmstcmFwaWRzLW1sCg=="
+alias = Alias(f"vector_type_{col_name_unique_tag}", f"vector_size_{col_name_unique_tag}",
+              f"vector_indices_{col_name_unique_tag}", f"cuml_values_{col_name_unique_tag}", "cuml_label",
+              "unique_id")
+Pred = namedtuple("Pred", ("prediction", "probability", "model_index", "raw_prediction"))
+pred = Pred("prediction", "probability", "model_index", "raw_prediction")
+ParamAlias = namedtuple("ParamAlias", ("cuml_init", "handle", "num_cols", "part_sizes", "loop",
+                                       "fit_multiple_params", "mem_config"))
+param_alias = ParamAlias("cuml_init", "handle", "num_cols", "part_sizes", "loop", "fit_multiple_params",
+                         "mem_config")
+
+FitInputType = List[Tuple[Any, Optional[Any], Optional[Any]]]
+_CumlFitFunc = Callable[[FitInputType, Dict[str, Any]], Dict[str, Any]]
+
+
+class _CumlCommon:
+    """reference: core.py:359-432."""
+
+    @staticmethod
+    def _get_gpu_device(context: Any, is_local: bool, is_transform: bool = False) -> int:
+        import torch
+
+        if is_local:
+            # local mode: partitionId doubles as the GPU id (core.py:377-384); transform wraps around
+            n = max(1, torch.cuda.device_count())
+            pid = context.partitionId() if context is not None else 0
+            return pid % n if is_transform else pid
+        from .utils import _get_gpu_id
+
+        return _get_gpu_id(context)
+
+    @staticmethod
+    def _set_gpu_device(context: Any, is_local: bool, is_transform: bool = False) -> int:
+        import torch
+
+        gpu_id = _CumlCommon._get_gpu_device(context, is_local, is_transform)
+        torch.cuda.set_device(gpu_id)
+        return gpu_id
+
+
+def _features_from_pdf(pdf: pd.DataFrame, multi_col_names: Optional[List[str]], appender: DeviceRowAppender,
+                       logger: Any) -> int:
+    """One Arrow batch -> rows of the device matrix.  Fast path: the Arrow child buffer, zero-copy.
+    Compat path (classic Spark conversion: object column of ndarrays): host stacking, as core.py:916 does."""
+    n_b = int(pdf.shape[0])
+    if n_b == 0:
+        return 0
+    if multi_col_names:
+        cols = []
+        for c in multi_col_names:
+            a = pdf[c].to_numpy()
+            if a.dtype == np.float64 or a.dtype == np.float32 or a.dtype.kind == "i":
+                cols.append(np.ascontiguousarray(a))
+            else:
+                cols.append(np.ascontiguousarray(a, dtype=np.float32))
+        dt = cols[0].dtype
+        cols = [c if c.dtype == dt else c.astype(dt) for c in cols]
+        appender.append_columns(cols)
+        return n_b
+    col = pdf[alias.data]
+    bufs = arrow_list_column_buffers(col)
+    if bufs is not None:
+        vals, offsets, n_rows = bufs
+        appender.append_values(vals, offsets, n_rows)
+    else:
+        stacked = np.array(list(col), order="C")  # reference idiom (core.py:916): slow, kept for compatibility
+        if stacked.ndim != 2:
+            raise ValueError("feature rows have different lengths")
+        if stacked.dtype not in (np.float32, np.float64):
+            stacked = stacked.astype(np.float32)
+        appender.append_values(np.ascontiguousarray(stacked).reshape(-1), None, n_b)
+    return n_b
+
+
+class _CumlCaller(_CumlParams, _CumlCommon):
+    """reference: core.py:435-1019."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._initialize_cuml_params()
+
+    # -- hooks a concrete estimator provides --
+    @abstractmethod
+    def _get_cuml_fit_func(self, dataset: Any, extra_params: Optional[List[Dict[str, Any]]] = None) -> _CumlFitFunc:
+        raise NotImplementedError
+
+    @abstractmethod
+    def _out_schema(self) -> Any:
+        raise NotImplementedError
+
+    def _require_nccl_ucx(self) -> Tuple[bool, bool]:
+        return (True, False)  # collectives only (core.py:564-571)
+
+    def _fit_array_order(self) -> str:
+        return "C"
+
+    def _validate_parameters(self) -> None:
+        """reference round-trips the params through the JVM estimator (core.py:579-602); without a JVM the
+        same constraints are checked here."""
+        cp = self.cuml_params
+        if "n_clusters" in cp and not (isinstance(cp["n_clusters"], int) and cp["n_clusters"] > 1):
+            raise ValueError(f"k given invalid value {cp['n_clusters']} (must be > 1)")
+        if "max_iter" in cp and cp["max_iter"] < 0:
+            raise ValueError(f"maxIter given invalid value {cp['max_iter']}")
+        if "tol" in cp and cp["tol"] < 0:
+            raise ValueError(f"tol given invalid value {cp['tol']}")
+
+    def _pre_process_data(self, dataset: LocalDataFrame) -> Tuple[LocalDataFrame, Optional[List[str]], int, str]:
+        """-> (selected/cast dataframe, multi_col_names, dimension, feature dtype)."""
+        input_col, input_cols = self._get_input_columns()
+        types = dict(dataset.dtypes)
+        if input_col is not None:
+            if input_col not in types:
+                raise ValueError(f"features column '{input_col}' not found in {dataset.columns}")
+            t = types[input_col]
+            if not t.startswith("array<"):
+                raise ValueError(f"column '{input_col}' has type {t}; expected array<float|double> "
+                                 "(VectorUDT columns need pyspark)")
+            df = dataset.select(input_col).withColumnRenamed(input_col, alias.data)
+            inner = t[len("array<"):-1]
+            if inner == "double" and self._float32_inputs:
+                df = df.cast_column(alias.data, pa.list_(pa.float32()))   # core.py:489-495
+                inner = "float"
+            elif inner not in ("float", "double"):
+                df = df.cast_column(alias.data, pa.list_(pa.float32() if self._float32_inputs else pa.float64()))
+                inner = "float" if self._float32_inputs else "double"
+            first = df.first()
+            if first is None:
+                raise RuntimeError("A python worker received no data.  Please increase amount of data or use fewer workers.")
+            dimension = len(first[alias.data])
+            return df, None, dimension, inner
+        assert input_cols is not None
+        for c in input_cols:
+            if c not in types:
+                raise ValueError(f"features column '{c}' not found in {dataset.columns}")
+        df = dataset.select(*input_cols)
+        for c in input_cols:  # core.py:543-557 casts every scalar column
+            want = pa.float32() if (self._float32_inputs or types[c] not in ("double",)) else pa.float64()
+            if types[c] == "double" and not self._float32_inputs:
+                want = pa.float64()
+            df = df.cast_column(c, want)
+        return df, list(input_cols), len(input_cols), "float"
+
+    def _call_cuml_fit_func(self, dataset: LocalDataFrame, partially_collect: bool = True,
+                            paramMaps: Optional[Sequence[Dict[Any, Any]]] = None) -> LocalDataFrame:
+        self._validate_parameters()
+        cls = self.__class__
+        df, multi_col_names, dimension, _ = self._pre_process_data(dataset)
+        num_workers = self.num_workers
+        if df.getNumPartitions() != num_workers:
+            df = df.repartition(num_workers)   # core.py:771-772
+        is_local = True
+        params: Dict[str, Any] = {param_alias.cuml_init: dict(self.cuml_params), param_alias.fit_multiple_params: None}
+        cuml_fit_func = self._get_cuml_fit_func(dataset, None)
+        (enable_nccl, require_ucx) = self._require_nccl_ucx()
+        cuml_verbose = self.cuml_params.get("verbose", False)
+
+        def _train_udf(pdf_iter: Iterator[pd.DataFrame]) -> Iterator[pd.DataFrame]:
+            from spark_rapids_ml_b200 import _native
+            from spark_rapids_ml_b200.common.cuml_context import CumlContext
+            from spark_rapids_ml_b200.sparkshim import BarrierTaskContext as _BTC
+
+            logger = get_logger(cls)
+            context = _BTC.get()
+            partition_id = context.partitionId()
+            gpu_id = _CumlCommon._set_gpu_device(context, is_local)
+            logger.info("Loading data into device memory (b2k_ingest_append)")
+            with CumlContext(partition_id, num_workers, context, enable_nccl, require_ucx, device=gpu_id) as cc:
+                appender = DeviceRowAppender(cc.handle, dimension)
+                sizes: List[int] = []
+                for pdf in pdf_iter:
+                    sizes.append(_features_from_pdf(pdf, multi_col_names, appender, logger))
+                if len(sizes) == 0 or all(sz == 0 for sz in sizes):
+                    raise RuntimeError(
+                        "A python worker received no data.  Please increase amount of data or use fewer workers.")
+                X = appender.finish()
+                inputs: FitInputType = [(X, None, None)]
+                params[param_alias.handle] = cc.handle
+                params[param_alias.part_sizes] = sizes
+                params[param_alias.num_cols] = dimension
+                params[param_alias.loop] = cc._loop
+                params[param_alias.mem_config] = {"cuda_managed_mem_enabled": False, "cuda_system_mem_enabled": False,
+                                                  "cuda_system_mem_headroom": None}
+                logger.info("Invoking fit")
+                import signal
+
+                if hasattr(signal, "SIGHUP"):
+                    try:
+                        signal.signal(signal.SIGHUP, signal.SIG_DFL)  # core.py:975-981
+                    except ValueError:
+                        pass  # not the main thread (in-process single-partition run)
+                result = cuml_fit_func(inputs, params)
+                logger.info("Fit complete")
+            if partially_collect:
+                if enable_nccl:
+                    context.barrier()
+                if context.partitionId() == 0:
+                    yield pd.DataFrame(data=result)
+            else:
+                yield pd.DataFrame(data=result)
+
+        return df.mapInPandas(_train_udf, schema=self._out_schema(), barrier=True)
+
+
+class _CumlEstimator(_CumlCaller):
+    """reference: core.py:1067-1311."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.logger = get_logger(self.__class__)
+
+    @abstractmethod
+    def _create_pyspark_model(self, result: Row) -> "_CumlModel":
+        raise NotImplementedError
+
+    def _merge_model_chunks(self, rows: List[Row], paramMaps: Optional[Sequence[Dict[Any, Any]]] = None) -> List[Row]:
+        return rows
+
+    def _fit_internal(self, dataset: LocalDataFrame, paramMaps: Optional[Sequence[Dict[Any, Any]]]) -> List["_CumlModel"]:
+        self.logger.info(f"Training spark-rapids-ml (b200) with {self.num_workers} worker(s) ...")
+        rows = self._call_cuml_fit_func(dataset=dataset, partially_collect=True, paramMaps=paramMaps).collect()
+        self.logger.info("Finished training")
+        rows = self._merge_model_chunks(rows, paramMaps)
+        models: List["_CumlModel"] = []
+        for index in range(1 if paramMaps is None else len(paramMaps)):
+            model = self._create_pyspark_model(rows[index])
+            model._num_workers = self._num_workers
+            model._float32_inputs = self._float32_inputs
+            self._copyValues(model, paramMaps[index] if paramMaps is not None else None)
+            self._copy_cuml_params(model)
+            models.append(model)
+        return models
+
+    def fit(self, dataset: LocalDataFrame, params: Optional[Dict[Any, Any]] = None) -> "_CumlModel":
+        est = self.copy(params) if params else self
+        return est._fit(dataset)
+
+    def _fit(self, dataset: LocalDataFrame) -> "_CumlModel":
+        if self._use_cpu_fallback():
+            # reference: core.py:1283-1295 falls back to pyspark.ml on CPU; this build has NO CPU path.
+            raise ValueError("a Spark Param without GPU support is set and spark_rapids_ml_b200 has no CPU fallback")
+        return self._fit_internal(dataset, None)[0]
+
+    # -- persistence (core.py:268-307) --
+    def save(self, path: str, overwrite: bool = True) -> None:
+        _save_metadata(self, path, overwrite)
+
+    def write(self) -> "_Writer":
+        return _Writer(self)
+
+    @classmethod
+    def load(cls, path: str) -> "_CumlEstimator":
+        meta = _load_metadata(path)
+        inst = cls()
+        inst.uid = meta["uid"]
+        _set_params_from_metadata(inst, meta)
+        return inst
+
+
+class _Writer:
+    def __init__(self, inst: Any):
+        self.inst = inst
+        self._overwrite = False
+
+    def overwrite(self) -> "_Writer":
+        self._overwrite = True
+        return self
+
+    def save(self, path: str) -> None:
+        self.inst.save(path, overwrite=self._overwrite)
+
+
+def _save_metadata(inst: Any, path: str, overwrite: bool, extra: Optional[Dict[str, Any]] = None) -> None:
+    if os.path.exists(path) and not overwrite:
+        raise IOError(f"Path {path} already exists. To overwrite it, use write().overwrite().save(path).")
+    os.makedirs(os.path.join(path, "metadata"), exist_ok=True)
+    meta = {
+        "class": inst.__module__ + "." + inst.__class__.__name__,
+        "uid": inst.uid,
+        "paramMap": {p.name: v for p, v in inst._paramMap.items()},
+        "defaultParamMap": {p.name: v for p, v in inst._defaultParamMap.items()},
+        "_cuml_params": inst._cuml_params,
+        "_num_workers": inst._num_workers,
+        "_float32_inputs": inst._float32_inputs,
+    }
+    if extra:
+        meta.update(extra)
+    with open(os.path.join(path, "metadata", "part-00000"), "w") as f:
+        f.write(json.dumps(meta))
+
+
+def _load_metadata(path: str) -> Dict[str, Any]:
+    with open(os.path.join(path, "metadata", "part-00000")) as f:
+        return json.loads(f.read())
+
+
+def _set_params_from_metadata(inst: Any, meta: Dict[str, Any]) -> None:
+    for name, v in meta.get("defaultParamMap", {}).items():
+        if inst.hasParam(name):
+            inst._setDefault(**{name: v})
+    for name, v in meta.get("paramMap", {}).items():
+        if inst.hasParam(name):
+            inst._set(**{name: v})
+    inst._cuml_params = meta["_cuml_params"]
+    inst._num_workers = meta["_num_workers"]
+    inst._float32_inputs = meta["_float32_inputs"]
+
+
+class _CumlModel(_CumlParams, _CumlCommon):
+    """reference: core.py:1356-1753 (KMeans-relevant subset)."""
+
+    def __init__(self, *, dtype: Optional[str] = None, n_cols: Optional[int] = None, **model_attributes: Any) -> None:
+        super().__init__()
+        self._initialize_cuml_params()
+        self.dtype = dtype
+        self.n_cols = n_cols
+        self._model_attributes = model_attributes
+        self._model_attributes["dtype"] = dtype
+        self._model_attributes["n_cols"] = n_cols
+
+    def _get_model_attributes(self) -> Optional[Dict[str, Any]]:
+        return self._model_attributes
+
+    @abstractmethod
+    def _get_cuml_transform_func(self, dataset: Any, eval_metric_info: Any = None) -> Tuple[Callable, Callable, Optional[Callable]]:
+        raise NotImplementedError
+
+    @abstractmethod
+    def _out_schema(self, input_schema: Any) -> Any:
+        raise NotImplementedError
+
+    # -- persistence (core.py:310-355) --
+    def save(self, path: str, overwrite: bool = True) -> None:
+        _save_metadata(self, path, overwrite)
+        os.makedirs(os.path.join(path, "data"), exist_ok=True)
+        with open(os.path.join(path, "data", "part-00000"), "w") as f:
+            f.write(json.dumps(self._get_model_attributes()))
+
+    def write(self) -> _Writer:
+        return _Writer(self)
+
+    @classmethod
+    def load(cls, path: str) -> "_CumlModel":
+        meta = _load_metadata(path)
+        with open(os.path.join(path, "data", "part-00000")) as f:
+            attrs = json.loads(f.read())
+        inst = cls(**attrs)
+        inst.uid = meta["uid"]
+        _set_params_from_metadata(inst, meta)
+        return inst
+
+    def transform(self, dataset: LocalDataFrame) -> LocalDataFrame:
+        return self._transform(dataset)
+
+
+class _CumlModelWithColumns(_CumlModel):
+    """reference: core.py:1797-1941 — keeps the input columns and appends the prediction column."""
+
+    def _transform(self, dataset: LocalDataFrame) -> LocalDataFrame:
+        input_col, input_cols = self._get_input_columns()
+        construct, transform_internal, _ = self._get_cuml_transform_func(dataset)
+        pred_name = self.getOrDefault("predictionCol")
+        types = dict(dataset.dtypes)
+        n_cols = self.n_cols
+        out_parts: List[List[pa.Array]] = []
+        state: Dict[str, Any] = {}
+        for pid, part in enumerate(dataset._parts):
+            arrs: List[pa.Array] = []
+            for batch in part:
+                if "model" not in state:
+                    gpu = _CumlCommon._set_gpu_device(BarrierTaskContext(pid, len(dataset._parts)), True, True)
+                    state["model"] = construct(gpu)
+                pdf = batch.to_pandas(types_mapper=pd.ArrowDtype) if dataset.arrow_backed_pandas else batch.to_pandas()
+                if input_cols:
+                    feats: Any = pdf[input_cols]
+                else:
+                    feats = pdf[[input_col]].rename(columns={input_col: alias.data})
+                res = transform_internal(state["model"], feats)
+                arrs.append(pa.array(np.asarray(res), type=pa.int32()))
+            out_parts.append(arrs)
+        if "model" in state and hasattr(state["model"], "close"):
+            state["model"].close()
+        assert n_cols is None or n_cols > 0
+        return dataset.with_appended_column(pred_name, out_parts)
+
+
+class _CumlModelWithPredictionCol(_CumlModelWithColumns):
+    """reference: core.py:1944-1967."""
+
+    def setPredictionCol(self, value: str) -> "_CumlModelWithPredictionCol":
+        self._set_params(predictionCol=value)
+        return self

@@ -69,6 +69,7 @@ extern "C" int b2k_ctx_destroy(b2k_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->nccl) b2k_comm_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->prof_dev) cudaFree(ctx->prof_dev);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->dev_stage[i]) cudaFree(ctx->dev_stage[i]);
@@ -91,6 +92,8 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
   } else if (k == "check_every") {
     if (value < 1) return b2k_fail(ctx, B2K_ERR_INVALID, "check_every must be >= 1");
     ctx->check_every = (int)value;
+  } else if (k == "profile_fused") {
+    ctx->profile_fused = value ? 1 : 0;
   } else if (k == "grid_limit") {
     if (value < 0) return b2k_fail(ctx, B2K_ERR_INVALID, "grid_limit must be >= 0");
     ctx->grid_limit = (int)value;

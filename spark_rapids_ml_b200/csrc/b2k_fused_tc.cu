@@ -52,7 +52,7 @@ struct Cfg {
   static_assert(DP % CHUNK == 0 && DP >= CHUNK && DP <= 256, "DP");
   static constexpr int NCH = DP / CHUNK;
   static constexpr int C_BYTES = KP * DP * 4;                  // one of Chi / Clo
-  static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64;
+  static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64 + 2048 /*sort*/;
   static constexpr int NSLOT_RAW = (int)((SMEM_LIMIT - 1024 - 2 * C_BYTES - MISC) / SLOT_BYTES);
   static constexpr int NSLOT = NSLOT_RAW > 12 ? 12 : NSLOT_RAW;
   static_assert(NSLOT >= NCH + 1, "ring too small");
@@ -78,10 +78,13 @@ struct Cfg {
   static constexpr int NBARS = B_CFULL + 1;
   static_assert(NBARS * 8 <= 512, "barrier area");
   static constexpr int OFF_TMEMPTR = OFF_BARS + 512;
-  static constexpr int SMEM_BYTES = OFF_TMEMPTR + 64 + 1024;  // +1024: manual 1 KB alignment slack
+  static constexpr int OFF_SORT = OFF_TMEMPTR + 64;            // counting-sort scratch (epilogue -> update)
+  static constexpr int SMEM_BYTES = OFF_SORT + 2048 + 1024;   // +1024: manual 1 KB alignment slack
   static_assert(SMEM_BYTES <= (int)SMEM_LIMIT, "smem");
   static constexpr int UPL = (DP / 4 + 31) / 32;   // float4 units per lane in the update warps
   static constexpr int CPW = (KP + N_UPD - 1) / N_UPD;  // clusters per update warp
+  static constexpr int KPL = (KP + 31) / 32;            // sort keys per lane in the epilogue scan
+  static_assert(KP % N_UPD == 0, "KP must be a multiple of the update warp count");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -100,12 +103,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // suspend-time hint (ns): the waiting warp sleeps in hardware instead of burning issue slots
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(200000u)
       : "memory");
   return ok;
 }
@@ -116,12 +120,18 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
+    if (++spins == (1u << 22)) mbar_timeout(bar, parity);
   }
+}
+
+// optional stage profiling (FusedArgs::prof != NULL): cycles spent blocked on a barrier are added to `acc`
+__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  if (!prof) { mbar_wait(bar, parity); return; }
+  long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
@@ -130,8 +140,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// warm L2 with a future tile so that the real load (which pins a shared-memory slot) sees L2 latency, not DRAM
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// one elected lane of a converged warp (ptxas emits single-issue UTC*/UTMA* instead of a per-lane waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -240,7 +265,9 @@ struct FusedArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int do_update;
+  int need_cost;           // compute ||x||^2, min distance and the cost partial (assign / inertia passes)
   const B2kLoopState* st;
+  long long* prof;         // [grid][NWARPS][8] cycle counters or NULL
 };
 
 template <int KP, int DP>
@@ -261,10 +288,15 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   float* xnorm_s = reinterpret_cast<float*>(gbase + G::OFF_XNORM);   // [2][128]
   const uint32_t bars = base + G::OFF_BARS;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(gbase + G::OFF_TMEMPTR);
+  uint8_t* sort_s = gbase + G::OFF_SORT;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool prof = args.prof != nullptr;
+  const bool need_cost = args.need_cost != 0;
+  long long pw[6] = {0, 0, 0, 0, 0, 0};   // blocked cycles per barrier kind (role specific)
+  const long long t_role0 = prof ? clock64() : 0;
 
   // ---- one-time setup ----
   if (warp == W_TMA && lane == 0) {
@@ -300,29 +332,48 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);   // provably warp-uniform
 
   const int tile0 = blockIdx.x;
   const int tstep = gridDim.x;
 
   if (warp == W_TMA) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar(G::B_CFULL), 2u * G::C_BYTES);
       for (int c = 0; c < G::NCH; ++c) {
         tma_load_2d(chi_s + c * (KP * 128), &mapChi, bar(G::B_CFULL), c * CHUNK, 0);
         tma_load_2d(clo_s + c * (KP * 128), &mapClo, bar(G::B_CFULL), c * CHUNK, 0);
       }
-      int xs = 0;
-      uint32_t xph = 0;
-      for (int tile = tile0; tile < args.ntiles; tile += tstep) {
+    }
+    __syncwarp();
+    int xs = 0;
+    uint32_t xph = 0;
+    constexpr int PF = 3;   // tiles of L2 look-ahead beyond what the ring already holds
+    if (elect_one()) {
+      for (int p = 0; p < PF + 2; ++p) {
+        const int pt = tile0 + p * tstep;
+        if (pt < args.ntiles)
+          for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
+      }
+    }
+    __syncwarp();
+    for (int tile = tile0; tile < args.ntiles; tile += tstep) {
+      if (elect_one()) {
+        const int pt = tile + (PF + 2) * tstep;
+        if (pt < args.ntiles)
+          for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
+      }
+      __syncwarp();
 #pragma unroll 1
-        for (int c = 0; c < G::NCH; ++c) {
-          mbar_wait(bar(G::B_XEMPTY + xs), xph ^ 1u);
+      for (int c = 0; c < G::NCH; ++c) {
+        mbar_wait_p(bar(G::B_XEMPTY + xs), xph ^ 1u, prof, pw[0]);
+        if (elect_one()) {
           mbar_expect_tx(bar(G::B_XFULL + xs), SLOT_BYTES);
           tma_load_2d(ring + xs * SLOT_BYTES, &mapX, bar(G::B_XFULL + xs), c * CHUNK, tile * TM);
-          if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
         }
+        __syncwarp();
+        if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
       }
     }
   } else if (warp == W_MMA) {
@@ -335,14 +386,14 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait(bar(G::B_DEMPTY + b), bph ^ 1u);
+      mbar_wait_p(bar(G::B_DEMPTY + b), bph ^ 1u, prof, pw[0]);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-        mbar_wait(bar(G::B_AFULL + as), aph);
+        mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = tmem_base + as * A_COLS;
           const uint32_t a_lo = a_hi + CHUNK;
           const uint32_t bhi = chi_s + c * (KP * 128);
@@ -377,8 +428,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       float xn = 0.f;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-        mbar_wait(bar(G::B_XFULL + xs), xph);
-        mbar_wait(bar(G::B_AEMPTY + as), aph ^ 1u);
+        mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
+        mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
         tc_fence_after();
         const uint32_t rowaddr = ring + xs * SLOT_BYTES + (uint32_t)r * 128u;
         uint32_t hi[32], lo[32];
@@ -392,7 +443,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
             float l = e[t] - __uint_as_float(hb);
             hi[j * 4 + t] = hb;
             lo[j * 4 + t] = rn_tf32_bits(l);
-            xn = fmaf(e[t], e[t], xn);
+            if (need_cost) xn = fmaf(e[t], e[t], xn);
           }
         }
         const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(as * A_COLS);
@@ -408,10 +459,12 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
         if (++as == NA) { as = 0; aph ^= 1u; }
       }
-      mbar_wait(bar(G::B_NEMPTY + b), bph ^ 1u);
-      xnorm_s[b * TM + r] = xn;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(G::B_NFULL + b));
+      if (need_cost) {
+        mbar_wait_p(bar(G::B_NEMPTY + b), bph ^ 1u, prof, pw[2]);
+        xnorm_s[b * TM + r] = xn;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(G::B_NFULL + b));
+      }
     }
   } else if (warp < W_UPD0) {
     // ======================= epilogue warps: TMEM D -> argmin =======================
@@ -423,7 +476,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait(bar(G::B_DFULL + b), bph);
+      mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
       tc_fence_after();
       float best = __int_as_float(0x7f800000);
       int bj = 0;
@@ -433,9 +486,15 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tmem_ld_x32(tmem_base + lane_field + (uint32_t)(D_OFF + b * KP + g * 32), v);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float dist = fmaf(-2.f, __uint_as_float(v[j]), cnorm_s[g * 32 + j]);
-          if (dist < best) { best = dist; bj = g * 32 + j; }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 cn4 = *reinterpret_cast<const float4*>(cnorm_s + g * 32 + j4 * 4);
+          const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = j4 * 4 + t;
+            float dist = fmaf(-2.f, __uint_as_float(v[j]), cn[t]);
+            if (dist < best) { best = dist; bj = g * 32 + j; }
+          }
         }
       }
       if constexpr (KP % 32 != 0) {
@@ -460,22 +519,74 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(G::B_DEMPTY + b));   // D buffer may be overwritten by tile ti+2
 
-      mbar_wait(bar(G::B_NFULL + b), bph);
-      const float xn = xnorm_s[b * TM + r];
       const int64_t grow = (int64_t)tile * TM + r;
       const bool valid = grow < args.n;
-      const float md = fmaxf(xn + best, 0.f);
-      mbar_wait(bar(G::B_LEMPTY + b), bph ^ 1u);
-      labels_s[b * TM + r] = valid ? bj : -1;
+      // ---- deterministic counting sort of the tile's rows by (owner update warp, owned-cluster slot, row) ----
+      // key = (label % 8) * CPW + label / 8: update warp u then owns the contiguous key range [u*CPW, (u+1)*CPW)
+      uint8_t* cnt = sort_s + (ti & 1) * 512;            // [4 warps][128] per-warp key histogram (parity buffered)
+      uint8_t* rows_sorted = sort_s + 1024 + b * 128;    // [128] row ids in key order
+      uint8_t* start = sort_s + 1280 + b * 192;          // [KP + 1] exclusive offsets per key
+      if (lane < KP / 4) reinterpret_cast<uint32_t*>(cnt + q * 128)[lane] = 0u;
+      __syncwarp();
+      const int key = valid ? ((bj & (N_UPD - 1)) * G::CPW + (bj >> 3)) : KP;
+      const uint32_t same = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      if (valid && rank == 0) cnt[q * 128 + key] = (uint8_t)__popc(same);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+      int tot[G::KPL];
+      int lane_sum = 0;
+#pragma unroll
+      for (int i = 0; i < G::KPL; ++i) {
+        const int kk = lane * G::KPL + i;
+        tot[i] = (kk < KP) ? (int)cnt[kk] + (int)cnt[128 + kk] + (int)cnt[256 + kk] + (int)cnt[384 + kk] : 0;
+        lane_sum += tot[i];
+      }
+      int incl = lane_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int st[G::KPL];
+      st[0] = incl - lane_sum;
+#pragma unroll
+      for (int i = 1; i < G::KPL; ++i) st[i] = st[i - 1] + tot[i - 1];
+      int my_start = 0;
+#pragma unroll
+      for (int i = 0; i < G::KPL; ++i) {
+        const int t = __shfl_sync(0xffffffffu, st[i], (key < KP ? key : 0) / G::KPL);
+        if ((key % G::KPL) == i) my_start = t;
+      }
+      int pos = my_start + rank;
       if (valid) {
-        if (args.labels_out) args.labels_out[grow] = bj;
-        if (args.mind_out) args.mind_out[grow] = md;
-        cost += (double)md;
+#pragma unroll
+        for (int q2 = 0; q2 < 3; ++q2)
+          if (q2 < q) pos += (int)cnt[q2 * 128 + key];
+      }
+      mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
+      if (valid) rows_sorted[pos] = (uint8_t)r;
+      if (q == 0) {
+#pragma unroll
+        for (int i = 0; i < G::KPL; ++i) {
+          const int kk = lane * G::KPL + i;
+          if (kk < KP) start[kk] = (uint8_t)st[i];
+        }
+        if (lane == 31) start[KP] = (uint8_t)incl;
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(G::B_LFULL + b));
-        mbar_arrive(bar(G::B_NEMPTY + b));
+      if (lane == 0) mbar_arrive(bar(G::B_LFULL + b));
+      // off the critical path: outputs and cost
+      if (valid && args.labels_out) args.labels_out[grow] = bj;
+      if (need_cost) {
+        mbar_wait_p(bar(G::B_NFULL + b), bph, prof, pw[1]);
+        const float xn = xnorm_s[b * TM + r];
+        const float md = fmaxf(xn + best, 0.f);
+        if (valid) {
+          if (args.mind_out) args.mind_out[grow] = md;
+          cost += (double)md;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(G::B_NEMPTY + b));
       }
     }
     // per-CTA cost: fixed-order fold (lanes, then the 4 warps through shared memory after the final sync)
@@ -499,68 +610,67 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait(bar(G::B_LFULL + b), bph);
-      // slots of this tile's chunks (observe their full barriers: TMA writes come from the async proxy)
+      mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
+      // slots of this tile's chunks.  Their x_full phases completed before the convert warps consumed them, which
+      // happens-before the MMA commit, the epilogue and hence this tile's lab_full: no need to poll them again.
       uint32_t slot_addr[G::NCH];
       {
         int s2 = xs;
-        uint32_t p2 = xph;
 #pragma unroll
         for (int c = 0; c < G::NCH; ++c) {
-          mbar_wait(bar(G::B_XFULL + s2), p2);
           slot_addr[c] = ring + s2 * SLOT_BYTES;
-          if (++s2 == G::NSLOT) { s2 = 0; p2 ^= 1u; }
+          if (++s2 == G::NSLOT) s2 = 0;
         }
       }
       if (args.do_update) {
-        int lab[4];
+        const uint8_t* rows_sorted = sort_s + 1024 + b * 128;
+        const uint8_t* start = sort_s + 1280 + b * 192;
+        // this lane's float4 units of a row: slot base + 16-B unit index inside the 128-B swizzle line
+        uint32_t unit_base[G::UPL];
+        uint32_t unit_j[G::UPL];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) lab[g] = labels_s[b * TM + g * 32 + lane];
+        for (int i = 0; i < G::UPL; ++i) {
+          const int unit = lane + 32 * i;
+          const int cc = unit >> 3;
+          uint32_t sa = slot_addr[0];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t m = __ballot_sync(0xffffffffu, lab[g] >= 0 && (lab[g] & (N_UPD - 1)) == u);
-          while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const int l = __shfl_sync(0xffffffffu, lab[g], bit);
-            const int row = g * 32 + bit;
-            const int cl = l >> 3;
-            float4 v[G::UPL];
+          for (int c2 = 1; c2 < G::NCH; ++c2) sa = (cc == c2) ? slot_addr[c2] : sa;
+          unit_base[i] = sa;
+          unit_j[i] = (uint32_t)(unit & 7);
+        }
+        auto load_row = [&](int row, float4 (&v)[G::UPL]) {
 #pragma unroll
-            for (int i = 0; i < G::UPL; ++i) {
-              const int unit = lane + 32 * i;          // float4 index within the row
-              if (unit < DP / 4) {
-                const int cc = unit >> 3, j = unit & 7;
-                // static chunk index for register-resident slot_addr[]: select with a small switch
-                uint32_t sa = slot_addr[0];
+          for (int i = 0; i < G::UPL; ++i) {
+            if (lane + 32 * i < DP / 4)
+              v[i] = lds128(unit_base[i] + (uint32_t)row * 128u + ((unit_j[i] ^ (uint32_t)(row & 7)) << 4));
+            else
+              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        // segment bounds of my CPW owned clusters: start[u*CPW .. u*CPW + CPW]
+        const int sv = (lane <= G::CPW) ? (int)start[u * G::CPW + lane] : 0;
 #pragma unroll
-                for (int c2 = 1; c2 < G::NCH; ++c2) sa = (cc == c2) ? slot_addr[c2] : sa;
-                v[i] = lds128(sa + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4));
-              } else {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < G::CPW; ++c) {
+          const int i0 = __shfl_sync(0xffffffffu, sv, c);
+          const int i1 = __shfl_sync(0xffffffffu, sv, c + 1);
+          cnt[c] += i1 - i0;
+          for (int i = i0; i < i1; i += 2) {      // rows of one cluster, ascending row order, two in flight
+            const bool two = (i + 1 < i1);
+            const int r0 = (int)rows_sorted[i];
+            const int r1 = (int)rows_sorted[two ? i + 1 : i];
+            float4 v0[G::UPL], v1[G::UPL];
+            load_row(r0, v0);
+            load_row(r1, v1);
+#pragma unroll
+            for (int k2 = 0; k2 < G::UPL; ++k2) {
+              acc[c][k2].x += v0[k2].x; acc[c][k2].y += v0[k2].y; acc[c][k2].z += v0[k2].z; acc[c][k2].w += v0[k2].w;
+            }
+            if (two) {
+#pragma unroll
+              for (int k2 = 0; k2 < G::UPL; ++k2) {
+                acc[c][k2].x += v1[k2].x; acc[c][k2].y += v1[k2].y; acc[c][k2].z += v1[k2].z; acc[c][k2].w += v1[k2].w;
               }
             }
-            // warp-uniform dispatch on the owned-cluster slot (keeps accumulators in registers)
-#define B2K_ACC_CASE(c)                                                         \
-  case c:                                                                       \
-    if constexpr (c < G::CPW) {                                                 \
-      _Pragma("unroll") for (int i = 0; i < G::UPL; ++i) {                      \
-        acc[c < G::CPW ? c : 0][i].x += v[i].x;                                 \
-        acc[c < G::CPW ? c : 0][i].y += v[i].y;                                 \
-        acc[c < G::CPW ? c : 0][i].z += v[i].z;                                 \
-        acc[c < G::CPW ? c : 0][i].w += v[i].w;                                 \
-      }                                                                         \
-      cnt[c < G::CPW ? c : 0]++;                                                \
-    }                                                                           \
-    break;
-            switch (cl) {
-              B2K_ACC_CASE(0) B2K_ACC_CASE(1) B2K_ACC_CASE(2) B2K_ACC_CASE(3)
-              B2K_ACC_CASE(4) B2K_ACC_CASE(5) B2K_ACC_CASE(6) B2K_ACC_CASE(7)
-              B2K_ACC_CASE(8) B2K_ACC_CASE(9) B2K_ACC_CASE(10) B2K_ACC_CASE(11)
-              B2K_ACC_CASE(12) B2K_ACC_CASE(13) B2K_ACC_CASE(14) B2K_ACC_CASE(15)
-              default: break;
-            }
-#undef B2K_ACC_CASE
           }
         }
       }
@@ -600,6 +710,11 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   }
 
   // ---- teardown ----
+  if (prof && lane == 0) {
+    long long* o = args.prof + ((size_t)blockIdx.x * NWARPS + warp) * 8;
+    o[0] = clock64() - t_role0;
+    for (int i = 0; i < 6; ++i) o[1 + i] = pw[i];
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -763,7 +878,15 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.labels_out = labels_out;
   a.mind_out = mindist_out;
   a.do_update = do_update ? 1 : 0;
+  a.need_cost = (!do_update || mindist_out != nullptr) ? 1 : 0;
   a.st = st;
+  a.prof = nullptr;
+  if (ctx->profile_fused) {
+    if (!ctx->prof_dev) B2K_CUDA_OK(ctx, cudaMalloc(&ctx->prof_dev, (size_t)1024 * NWARPS * 8 * sizeof(long long)));
+    B2K_CUDA_OK(ctx, cudaMemsetAsync(ctx->prof_dev, 0, (size_t)plan.grid * NWARPS * 8 * sizeof(long long), s));
+    a.prof = ctx->prof_dev;
+    ctx->prof_grid = plan.grid;
+  }
 
   int rc = B2K_ERR_UNSUPPORTED;
 #define B2K_DISPATCH(KP_, DP_) \
@@ -784,5 +907,18 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   B2K_TRY(rc);
   ctx->stats.kernel_launches++;
   ctx->stats.fused_tc_launches++;
+  return B2K_OK;
+}
+
+// diagnostics: per-role blocked-cycle counters of the last fused launch (option "profile_fused" = 1)
+extern "C" int b2k_get_fused_profile(b2k_ctx* ctx, long long* out, int64_t cap, int* grid_out, int* warps_out) {
+  if (!ctx || !out) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_get_fused_profile: NULL argument");
+  if (!ctx->prof_dev || ctx->prof_grid == 0) return b2k_fail(ctx, B2K_ERR_STATE, "no fused profile recorded");
+  size_t cnt = (size_t)ctx->prof_grid * NWARPS * 8;
+  if ((int64_t)cnt > cap) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_get_fused_profile: buffer too small");
+  B2K_CUDA_OK(ctx, cudaDeviceSynchronize());
+  B2K_CUDA_OK(ctx, cudaMemcpy(out, ctx->prof_dev, cnt * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (grid_out) *grid_out = ctx->prof_grid;
+  if (warps_out) *warps_out = NWARPS;
   return B2K_OK;
 }

@@ -196,12 +196,13 @@ def test_large_shape_properties(ctx, path):
     C2 = C0.clone()
     ctx.kmeans_lloyd(X, C2, 1, 0.0)
     assert torch.equal(C1, C2)
-    # run to convergence, then one more step is a fixed point (idempotence)
-    C3 = C0.clone()
-    ctx.kmeans_lloyd(X, C3, 100, 1e-12)
+    # run to convergence from a near-optimal start, then one more step is a fixed point (idempotence)
+    C3 = (ctr + 0.3 * torch.randn((k, d), generator=g, device="cuda")).contiguous()
+    n_conv, _ = ctx.kmeans_lloyd(X, C3, 60, 1e-12)
+    assert n_conv < 60
     C4 = C3.clone()
     _, shift2 = ctx.kmeans_lloyd(X, C4, 1, 0.0)
-    assert shift2 <= 1e-8
+    assert shift2 <= 1e-10
     # spot-check 20k rows of the final labelling against the oracle
     idx = torch.randperm(n, generator=g, device="cuda")[:20000]
     lab, _ = ctx.kmeans_assign(X[idx].contiguous(), C3)
