@@ -192,7 +192,7 @@ class Context:
 
     def fused_profile(self) -> "np.ndarray":
         """[grid, warps, 8] int64 cycle counters of the last fused launch (needs option profile_fused=1)."""
-        buf = np.zeros(1024 * 18 * 8, dtype=np.int64)
+        buf = np.zeros(1024 * 32 * 8, dtype=np.int64)
         g, w = ctypes.c_int(0), ctypes.c_int(0)
         self._check(self._L.b2k_get_fused_profile(self._h, buf.ctypes.data, buf.size, ctypes.byref(g), ctypes.byref(w)))
         return buf[: g.value * w.value * 8].reshape(g.value, w.value, 8)

@@ -92,6 +92,8 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
   } else if (k == "check_every") {
     if (value < 1) return b2k_fail(ctx, B2K_ERR_INVALID, "check_every must be >= 1");
     ctx->check_every = (int)value;
+  } else if (k == "probe") {
+    ctx->probe = (int)value;
   } else if (k == "profile_fused") {
     ctx->profile_fused = value ? 1 : 0;
   } else if (k == "grid_limit") {

@@ -265,6 +265,7 @@ struct FusedArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int do_update;
+  int probe;               // EXPERIMENT 3: update warps ignore lab_full/lab_empty (stale row lists; WRONG sums)
   int need_cost;           // compute ||x||^2, min distance and the cost partial (assign / inertia passes)
   const B2kLoopState* st;
   long long* prof;         // [grid][NWARPS][8] cycle counters or NULL
@@ -439,10 +440,13 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            uint32_t hb = rn_tf32_bits(e[t]);
-            float l = e[t] - __uint_as_float(hb);
-            hi[j * 4 + t] = hb;
-            lo[j * 4 + t] = rn_tf32_bits(l);
+            // The tensor core TRUNCATES fp32 operands to tf32 (tools/probe_trunc.py), so adding half a tf32 ulp
+            // to the stored bits makes the hardware's truncation a round-to-nearest: no explicit mask needed on
+            // the stored words; only the value used to form `lo` is masked.
+            const uint32_t hs = __float_as_uint(e[t]) + 0x1000u;
+            const float l = e[t] - __uint_as_float(hs & 0xffffe000u);   // exact
+            hi[j * 4 + t] = hs;
+            lo[j * 4 + t] = __float_as_uint(l) + 0x1000u;
             if (need_cost) xn = fmaf(e[t], e[t], xn);
           }
         }
@@ -563,7 +567,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         for (int q2 = 0; q2 < 3; ++q2)
           if (q2 < q) pos += (int)cnt[q2 * 128 + key];
       }
-      mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
+      if (args.probe != 3) mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
       if (valid) rows_sorted[pos] = (uint8_t)r;
       if (q == 0) {
 #pragma unroll
@@ -610,16 +614,18 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
+      if (args.probe != 3) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
       // slots of this tile's chunks.  Their x_full phases completed before the convert warps consumed them, which
       // happens-before the MMA commit, the epilogue and hence this tile's lab_full: no need to poll them again.
       uint32_t slot_addr[G::NCH];
       {
         int s2 = xs;
+        uint32_t p2 = xph;
 #pragma unroll
         for (int c = 0; c < G::NCH; ++c) {
+          if (args.probe == 3) mbar_wait_p(bar(G::B_XFULL + s2), p2, prof, pw[1]);
           slot_addr[c] = ring + s2 * SLOT_BYTES;
-          if (++s2 == G::NSLOT) s2 = 0;
+          if (++s2 == G::NSLOT) { s2 = 0; p2 ^= 1u; }
         }
       }
       if (args.do_update) {
@@ -878,6 +884,7 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.labels_out = labels_out;
   a.mind_out = mindist_out;
   a.do_update = do_update ? 1 : 0;
+  a.probe = ctx->probe;
   a.need_cost = (!do_update || mindist_out != nullptr) ? 1 : 0;
   a.st = st;
   a.prof = nullptr;

@@ -37,6 +37,7 @@ struct b2k_ctx {
   int time_kernels = 0;
   int check_every = 4;
   int grid_limit = 0;
+  int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
   int profile_fused = 0;         // record per-role blocked-cycle counters of the fused kernel
   long long* prof_dev = nullptr;  // [grid][18 warps][8]
   int prof_grid = 0;

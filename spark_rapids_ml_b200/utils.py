@@ -78,7 +78,8 @@ def arrow_list_column_buffers(col: pd.Series) -> Optional[Tuple[np.ndarray, np.n
     if not isinstance(dt, pd.ArrowDtype):
         return None
     arr = col.array._pa_array if hasattr(col.array, "_pa_array") else pa.chunked_array(col.array)
-    arr = arr.combine_chunks() if isinstance(arr, pa.ChunkedArray) else arr
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.chunk(0) if arr.num_chunks == 1 else arr.combine_chunks()   # single chunk: stay zero-copy
     t = arr.type
     if arr.null_count:
         raise ValueError("null feature rows are not supported")

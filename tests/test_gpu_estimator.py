@@ -1,0 +1,89 @@
+"""End-to-end through the reference-facing surface on the GPU: KMeans(...).fit(df) / KMeansModel.transform(df)
+over Arrow batches — the reference's toy integration tests (python/tests/test_kmeans.py:202-282, 420-526)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import kmeans_oracle as ko
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture()
+def session():
+    from spark_rapids_ml_b200.sparkshim import LocalSession
+
+    return LocalSession({"spark.sql.execution.arrow.maxRecordsPerBatch": "3", "spark.rapids.ml.num_workers.local": "1"})
+
+
+@pytest.mark.parametrize("arrow_backed", [True, False])
+def test_reference_toy_cases_fit_transform_persist(session, tmp_path, arrow_backed):
+    from spark_rapids_ml_b200.clustering import KMeans, KMeansModel
+
+    for case in json.load(open(os.path.join(GOLD, "kmeans_known_answers.json")))["cases"]:
+        df = session.createDataFrame([(r,) for r in case["data"]], ["features"])
+        df.arrow_backed_pandas = arrow_backed
+        for init_mode in ("k-means||", "random"):
+            hits = 0
+            for seed in range(4):
+                km = KMeans(k=case["k"], maxIter=case["max_iter"], tol=case["tol"], seed=seed, initMode=init_mode,
+                            num_workers=1).setFeaturesCol("features")
+                model = km.fit(df)
+                assert model.dtype == "float32" and model.n_cols == 2 and model.hasSummary is False
+                C = sorted(c.tolist() for c in model.clusterCenters())
+                if np.allclose(C, case["expected_sorted_centers"], rtol=max(case["rel_tol"], 1e-7)):
+                    hits += 1
+                    out = model.setPredictionCol("newPrediction").transform(df)
+                    assert sorted(out.columns) == ["features", "newPrediction"]
+                    lab = [r["newPrediction"] for r in out.collect()]
+                    for a, b in case["same_label_pairs"]:
+                        assert lab[a] == lab[b]
+                    for a, b in case["diff_label_pairs"]:
+                        assert lab[a] != lab[b]
+                    p = str(tmp_path / f"m_{case['name']}_{init_mode.strip('|')}_{seed}_{arrow_backed}")
+                    model.write().overwrite().save(p)
+                    again = KMeansModel.load(p)
+                    assert again.cluster_centers_ == model.cluster_centers_
+                    assert model.predict(case["data"][0]) == lab[0]
+            assert hits >= 2, (case["name"], init_mode)
+
+
+def test_fit_layouts_agree_with_oracle(session):
+    """array<float>, array<double> (cast by float32_inputs) and multi-column layouts; many small Arrow batches."""
+    import pandas as pd
+
+    from spark_rapids_ml_b200.clustering import KMeans
+
+    session.conf.set("spark.sql.execution.arrow.maxRecordsPerBatch", "257")
+    X, _ = ko.make_blobs(3000, 12, 4, seed=5)
+    ref = None
+    for layout in ("array_f32", "array_f64", "multi_cols"):
+        if layout == "array_f32":
+            df = session.from_numpy(X)
+            km = KMeans(k=4, maxIter=30, seed=1, initMode="k-means||", num_workers=1)
+        elif layout == "array_f64":
+            df = session.from_numpy(X.astype(np.float64))
+            km = KMeans(k=4, maxIter=30, seed=1, initMode="k-means||", num_workers=1)
+        else:
+            cols = [f"c{i}" for i in range(12)]
+            df = session.createDataFrame(pd.DataFrame(X.astype(np.float64), columns=cols))
+            km = KMeans(k=4, maxIter=30, seed=1, initMode="k-means||", num_workers=1).setFeaturesCols(cols)
+        model = km.fit(df)
+        C = np.array(sorted(c.tolist() for c in model.clusterCenters()))
+        if ref is None:
+            ref = C
+        np.testing.assert_allclose(C, ref, rtol=1e-5, atol=1e-6)
+        lab = np.array([r["prediction"] for r in model.transform(df).collect()])
+        cmp = ko.compare_labels(X, np.array(model.cluster_centers_, dtype=np.float32), lab)
+        assert cmp["n_mismatch_outside_margin"] == 0
+
+
+def test_empty_partition_raises(session):
+    from spark_rapids_ml_b200.clustering import KMeans
+
+    df = session.from_numpy(np.zeros((0, 4), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="no data"):
+        KMeans(k=2, num_workers=1).fit(df)

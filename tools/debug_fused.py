@@ -30,7 +30,10 @@ def run(n, d, k, gen="blobs", path=2):
     # one lloyd step
     C1 = Cd.clone()
     n_it, shift = ctx.kmeans_lloyd(Xd, C1, 1, -1.0)
-    Cn, w, sh = ko.lloyd_iteration([X], C)
+    # expected next centers from the DEVICE labels (tie rows inside the 1e-6 margin may legitimately differ from the oracle)
+    S, w = ko.partial_sums(X, lab, k)
+    Cn = C.astype(np.float64); Cn[w > 0] = S[w > 0] / w[w > 0][:, None]; Cn = Cn.astype(np.float32)
+    sh = float(((Cn.astype(np.float64) - C.astype(np.float64)) ** 2).sum())
     err = ko.max_center_rel_err(C1.cpu().numpy(), Cn)
     print(f"   lloyd step: n_it={n_it} shift={shift:.6e} oracle_shift={sh:.6e} center_rel_err={err:.2e} stats={ctx.stats()}", flush=True)
     ctx.close()
