@@ -84,6 +84,7 @@ def test_fit_layouts_agree_with_oracle(session):
 def test_empty_partition_raises(session):
     from spark_rapids_ml_b200.clustering import KMeans
 
-    df = session.from_numpy(np.zeros((0, 4), dtype=np.float32))
+    df = session.from_numpy(np.zeros((3, 4), dtype=np.float32), num_partitions=1)
+    df._parts = [[]]                      # a partition whose Arrow stream is empty (core.py:959-962)
     with pytest.raises(RuntimeError, match="no data"):
         KMeans(k=2, num_workers=1).fit(df)
