@@ -104,7 +104,8 @@ const char* b2k_last_error(const b2k_ctx* ctx);
 int b2k_ctx_create(int device, b2k_ctx** out);
 int b2k_ctx_destroy(b2k_ctx* ctx);
 /* Options: "kernel_path" (b2k_kernel_path), "time_kernels" (0/1), "check_every" (iterations between host
- * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "profile_fused" (0/1). */
+ * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "profile_fused" (0/1),
+ * "pair" (1 = use the CTA-pair tcgen05 cta_group::2 kernel where instantiated, default 1). */
 int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value);
 int b2k_get_stats(const b2k_ctx* ctx, b2k_stats* out);
 /* Diagnostics (option "profile_fused"=1): per-CTA, per-warp-role cycle counters of the last fused launch,

@@ -94,6 +94,8 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->check_every = (int)value;
   } else if (k == "probe") {
     ctx->probe = (int)value;
+  } else if (k == "pair") {
+    ctx->pair = value ? 1 : 0;
   } else if (k == "profile_fused") {
     ctx->profile_fused = value ? 1 : 0;
   } else if (k == "grid_limit") {
@@ -262,7 +264,9 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
           ev.push_back(e1);
           B2K_CUDA_OK(ctx, cudaEventRecord(e0, s));
         }
-        B2K_TRY(b2k_launch_fused(ctx, B.plan, B.plan_scratch, X, n, d, C, k, nullptr, nullptr, true, B.st, s));
+        // cluster sizes of the previous iteration (R = [k*d sums | k counts | cost]) drive the update-warp balancing
+        B2K_TRY(b2k_launch_fused(ctx, B.plan, B.plan_scratch, X, n, d, C, k, nullptr, nullptr, true, B.st, s,
+                                 launched > 0 ? B.R + (size_t)k * d : nullptr));
         if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(e1, s));
         float* partials;
         int32_t* counts;

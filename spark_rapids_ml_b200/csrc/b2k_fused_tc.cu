@@ -46,12 +46,16 @@ constexpr int N_UPD = 8;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-template <int KP, int DP>
+template <int KP, int DP, bool PAIR = false>
 struct Cfg {
+  // PAIR: two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256 = 2 x 128 rows, one row tile per
+  // CTA); each CTA keeps only HALF of the centre rows in shared memory (the pair supplies B jointly), which
+  // frees KP*DP*4 bytes per CTA for two more ring slots and halves the B-operand shared-memory reads.
+  static constexpr int KPS = PAIR ? KP / 2 : KP;               // centre rows resident in this CTA's smem
   static_assert(KP % 16 == 0 && KP >= 16 && KP <= 128, "KP");
   static_assert(DP % CHUNK == 0 && DP >= CHUNK && DP <= 256, "DP");
   static constexpr int NCH = DP / CHUNK;
-  static constexpr int C_BYTES = KP * DP * 4;                  // one of Chi / Clo
+  static constexpr int C_BYTES = KPS * DP * 4;                 // one of Chi / Clo (this CTA's share)
   static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64 + 2048 /*sort*/;
   static constexpr int NSLOT_RAW = (int)((SMEM_LIMIT - 1024 - 2 * C_BYTES - MISC) / SLOT_BYTES);
   static constexpr int NSLOT = NSLOT_RAW > 12 ? 12 : NSLOT_RAW;
@@ -210,6 +214,58 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // round-to-nearest (ties away) fp32 -> tf32 (10 explicit mantissa bits), result has the low 13 bits clear
 __device__ __forceinline__ uint32_t rn_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
+// ---- CTA-pair (cluster of 2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  // relaxed: what these signals order is TMEM traffic (tcgen05.wait::st/ld + tcgen05.fence::before_thread_sync on
+  // this side, tcgen05.fence::after_thread_sync on the consumer side), not generic-proxy memory — a cluster-scope
+  // release here costs several hundred cycles per hand-off (measured).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins == (1u << 22)) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // signals the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_tf32_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -251,6 +307,37 @@ __global__ void __launch_bounds__(256) k_prep_centers_tc(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// cluster -> (update warp, accumulator slot) table.  The update stage is gated by its most loaded warp, so the
+// clusters are dealt to the 8 update warps by size (descending, snake order: a deterministic LPT-style packing
+// with exactly KP/8 slots per warp).  Sizes = the previous iteration's cluster counts (any positive scaling);
+// without them (first pass) the mapping is the identity j -> (j % 8, j / 8).
+//   keytab[j]  = owner_warp * CPW + slot        inv[key] = j
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_balance_table(const double* __restrict__ counts, int k, int KP,
+                                                       uint8_t* __restrict__ keytab, uint8_t* __restrict__ inv,
+                                                       const B2kLoopState* st) {
+  if (st != nullptr && st->done) return;
+  __shared__ double w[128];
+  const int j = threadIdx.x;
+  const int CPW = KP / N_UPD;
+  if (j < KP) w[j] = (counts != nullptr && j < k) ? counts[j] : -1.0 - (double)0;   // padding clusters sort last
+  __syncthreads();
+  if (j >= KP) return;
+  int key;
+  if (counts == nullptr) {
+    key = (j % N_UPD) * CPW + j / N_UPD;
+  } else {
+    int rank = 0;   // position in (count desc, index asc) order
+    for (int i = 0; i < KP; ++i) rank += (w[i] > w[j]) || (w[i] == w[j] && i < j);
+    const int round = rank / N_UPD, pos = rank % N_UPD;
+    const int owner = (round & 1) ? (N_UPD - 1 - pos) : pos;
+    key = owner * CPW + round;
+  }
+  keytab[j] = (uint8_t)key;
+  inv[key] = (uint8_t)j;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 struct FusedArgs {
@@ -259,6 +346,8 @@ struct FusedArgs {
   int k;
   int d;
   const float* cnorm;      // [KP]
+  const uint8_t* keytab;   // [KP] cluster -> sort key (owner update warp * CPW + slot)
+  const uint8_t* keyinv;   // [KP] sort key -> cluster
   float* partials;         // [grid][k*d]
   int32_t* counts;         // [grid][k]
   double* cost_partials;   // [grid]
@@ -271,11 +360,11 @@ struct FusedArgs {
   long long* prof;         // [grid][NWARPS][8] cycle counters or NULL
 };
 
-template <int KP, int DP>
+template <int KP, int DP, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapChi,
                       const __grid_constant__ CUtensorMap mapClo, const FusedArgs args) {
-  using G = Cfg<KP, DP>;
+  using G = Cfg<KP, DP, PAIR>;
   if (args.st != nullptr && args.st->done) return;
 
   extern __shared__ uint8_t smem_raw[];
@@ -309,12 +398,12 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       mbar_init(bar(G::B_XEMPTY + i), 4 + N_UPD);
     }
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar(G::B_AFULL + i), 4);
+      mbar_init(bar(G::B_AFULL + i), PAIR ? 8 : 4);       // PAIR: the convert warps of BOTH CTAs feed the leader
       mbar_init(bar(G::B_AEMPTY + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(G::B_DFULL + i), 1);
-      mbar_init(bar(G::B_DEMPTY + i), 4);
+      mbar_init(bar(G::B_DEMPTY + i), PAIR ? 8 : 4);
       mbar_init(bar(G::B_LFULL + i), 4);
       mbar_init(bar(G::B_LEMPTY + i), N_UPD);
       mbar_init(bar(G::B_NFULL + i), 4);
@@ -324,27 +413,47 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int j = threadIdx.x; j < KP; j += NTHREADS) cnorm_s[j] = args.cnorm[j];
+  uint8_t* keytab_s = sort_s + 1792;   // [KP]
+  uint8_t* keyinv_s = sort_s + 1920;   // [KP]
+  for (int j = threadIdx.x; j < KP; j += NTHREADS) { keytab_s[j] = args.keytab[j]; keyinv_s[j] = args.keyinv[j]; }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // peer barriers initialised / TMEM allocated before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);   // provably warp-uniform
 
-  const int tile0 = blockIdx.x;
-  const int tstep = gridDim.x;
+  // static tile schedule.  PAIR: cluster q handles tile pairs q, q+nclusters, ...; CTA rank r takes tile 2*pair+r
+  // (a trailing odd tile leaves the peer an all-out-of-range tile: TMA zero-fills it, every row is invalid).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int sched0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int sched_n = PAIR ? (args.ntiles + 1) / 2 : args.ntiles;
+  const int nit = sched0 < sched_n ? (sched_n - sched0 + sched_step - 1) / sched_step : 0;
+  auto tile_of = [&](int it) -> int {
+    const int sidx = sched0 + it * sched_step;
+    return PAIR ? 2 * sidx + (int)rank : sidx;
+  };
 
   if (warp == W_TMA) {
     // ======================= TMA producer =======================
     if (elect_one()) {
       mbar_expect_tx(bar(G::B_CFULL), 2u * G::C_BYTES);
-      for (int c = 0; c < G::NCH; ++c) {
-        tma_load_2d(chi_s + c * (KP * 128), &mapChi, bar(G::B_CFULL), c * CHUNK, 0);
-        tma_load_2d(clo_s + c * (KP * 128), &mapClo, bar(G::B_CFULL), c * CHUNK, 0);
+      for (int c = 0; c < G::NCH; ++c) {   // PAIR: this CTA's half of the centre rows
+        tma_load_2d(chi_s + c * (G::KPS * 128), &mapChi, bar(G::B_CFULL), c * CHUNK, (int)rank * G::KPS);
+        tma_load_2d(clo_s + c * (G::KPS * 128), &mapClo, bar(G::B_CFULL), c * CHUNK, (int)rank * G::KPS);
       }
     }
     __syncwarp();
@@ -353,16 +462,17 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     constexpr int PF = 3;   // tiles of L2 look-ahead beyond what the ring already holds
     if (elect_one()) {
       for (int p = 0; p < PF + 2; ++p) {
-        const int pt = tile0 + p * tstep;
-        if (pt < args.ntiles)
+        const int pt = tile_of(p);
+        if (p < nit && pt < args.ntiles)
           for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
       }
     }
     __syncwarp();
-    for (int tile = tile0; tile < args.ntiles; tile += tstep) {
+    for (int ti = 0; ti < nit; ++ti) {
+      const int tile = tile_of(ti);
       if (elect_one()) {
-        const int pt = tile + (PF + 2) * tstep;
-        if (pt < args.ntiles)
+        const int pt = tile_of(ti + PF + 2);
+        if (ti + PF + 2 < nit && pt < args.ntiles)
           for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
       }
       __syncwarp();
@@ -379,36 +489,48 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     }
   } else if (warp == W_MMA) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc_tf32(TM, KP);
+    constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 2 * TM : TM, KP);
     mbar_wait(bar(G::B_CFULL), 0);
     int as = 0;
     uint32_t aph = 0;
-    int ti = 0;
-    for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
+    for (int ti = 0; ti < ((PAIR && rank != 0) ? 0 : nit); ++ti) {   // PAIR: only the leader CTA issues
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait_p(bar(G::B_DEMPTY + b), bph ^ 1u, prof, pw[0]);
+      if constexpr (PAIR) mbar_wait_cluster(bar(G::B_DEMPTY + b), bph ^ 1u);
+      else mbar_wait_p(bar(G::B_DEMPTY + b), bph ^ 1u, prof, pw[0]);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-        mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
+        if constexpr (PAIR) mbar_wait_cluster(bar(G::B_AFULL + as), aph);
+        else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_hi = tmem_base + as * A_COLS;
           const uint32_t a_lo = a_hi + CHUNK;
-          const uint32_t bhi = chi_s + c * (KP * 128);
-          const uint32_t blo = clo_s + c * (KP * 128);
+          const uint32_t bhi = chi_s + c * (G::KPS * 128);
+          const uint32_t blo = clo_s + c * (G::KPS * 128);
 #pragma unroll
           for (int ks = 0; ks < CHUNK / 8; ++ks) {
             const uint64_t dhi = make_kmajor_sw128_desc(bhi + ks * 32);
             const uint64_t dlo = make_kmajor_sw128_desc(blo + ks * 32);
-            tc_mma_ts_tf32(d_tmem, a_lo + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u);  // small terms first
-            tc_mma_ts_tf32(d_tmem, a_hi + ks * 8, dlo, idesc, 1u);
-            tc_mma_ts_tf32(d_tmem, a_hi + ks * 8, dhi, idesc, 1u);
+            if constexpr (PAIR) {
+              tc_mma_ts_tf32_pair(d_tmem, a_lo + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u);
+              tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dlo, idesc, 1u);
+              tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dhi, idesc, 1u);
+            } else {
+              tc_mma_ts_tf32(d_tmem, a_lo + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u);  // small terms first
+              tc_mma_ts_tf32(d_tmem, a_hi + ks * 8, dlo, idesc, 1u);
+              tc_mma_ts_tf32(d_tmem, a_hi + ks * 8, dhi, idesc, 1u);
+            }
           }
-          tc_commit(bar(G::B_AEMPTY + as));
-          if (c == G::NCH - 1) tc_commit(bar(G::B_DFULL + b));
+          if constexpr (PAIR) {
+            tc_commit_pair(bar(G::B_AEMPTY + as));
+            if (c == G::NCH - 1) tc_commit_pair(bar(G::B_DFULL + b));
+          } else {
+            tc_commit(bar(G::B_AEMPTY + as));
+            if (c == G::NCH - 1) tc_commit(bar(G::B_DFULL + b));
+          }
         }
         __syncwarp();
         if (++as == NA) { as = 0; aph ^= 1u; }
@@ -422,8 +544,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t swz = (uint32_t)(r & 7);
     int xs = 0, as = 0;
     uint32_t xph = 0, aph = 0;
-    int ti = 0;
-    for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
+    // PAIR: this CTA's centre half must have landed before its first a_full signal reaches the leader
+    if constexpr (PAIR) mbar_wait(bar(G::B_CFULL), 0);
+    for (int ti = 0; ti < nit; ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       float xn = 0.f;
@@ -457,7 +580,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar(G::B_AFULL + as));
+          if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_AFULL + as), 0u);
+          else mbar_arrive(bar(G::B_AFULL + as));
           mbar_arrive(bar(G::B_XEMPTY + xs));
         }
         if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
@@ -476,8 +600,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const int r = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     double cost = 0.0;
-    int ti = 0;
-    for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
+    for (int ti = 0; ti < nit; ++ti) {
+      const int tile = tile_of(ti);
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
@@ -521,18 +645,21 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(G::B_DEMPTY + b));   // D buffer may be overwritten by tile ti+2
+      if (lane == 0) {   // D buffer may be overwritten by tile ti+2
+        if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_DEMPTY + b), 0u);
+        else mbar_arrive(bar(G::B_DEMPTY + b));
+      }
 
       const int64_t grow = (int64_t)tile * TM + r;
       const bool valid = grow < args.n;
       // ---- deterministic counting sort of the tile's rows by (owner update warp, owned-cluster slot, row) ----
-      // key = (label % 8) * CPW + label / 8: update warp u then owns the contiguous key range [u*CPW, (u+1)*CPW)
+      // key = keytab[label] (size-balanced, see k_balance_table): update warp u owns the key range [u*CPW, (u+1)*CPW)
       uint8_t* cnt = sort_s + (ti & 1) * 512;            // [4 warps][128] per-warp key histogram (parity buffered)
       uint8_t* rows_sorted = sort_s + 1024 + b * 128;    // [128] row ids in key order
       uint8_t* start = sort_s + 1280 + b * 192;          // [KP + 1] exclusive offsets per key
       if (lane < KP / 4) reinterpret_cast<uint32_t*>(cnt + q * 128)[lane] = 0u;
       __syncwarp();
-      const int key = valid ? ((bj & (N_UPD - 1)) * G::CPW + (bj >> 3)) : KP;
+      const int key = valid ? (int)keytab_s[bj] : KP;
       const uint32_t same = __match_any_sync(0xffffffffu, key);
       const int rank = __popc(same & ((1u << lane) - 1u));
       if (valid && rank == 0) cnt[q * 128 + key] = (uint8_t)__popc(same);
@@ -610,8 +737,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     }
     int xs = 0;
     uint32_t xph = 0;
-    int ti = 0;
-    for (int tile = tile0; tile < args.ntiles; tile += tstep, ++ti) {
+    for (int ti = 0; ti < nit; ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       if (args.probe != 3) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
@@ -699,7 +825,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       float* out = args.partials + (size_t)blockIdx.x * args.k * args.d;
 #pragma unroll
       for (int c = 0; c < G::CPW; ++c) {
-        const int l = u + N_UPD * c;
+        const int l = (int)keyinv_s[u * G::CPW + c];
         if (l < args.k) {
 #pragma unroll
           for (int i = 0; i < G::UPL; ++i) {
@@ -727,10 +853,15 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const double* cw = reinterpret_cast<const double*>(gbase + G::OFF_TMEMPTR + 16);
     args.cost_partials[blockIdx.x] = ((cw[0] + cw[1]) + cw[2]) + cw[3];
   }
+  if constexpr (PAIR) cluster_sync_all();   // the peer may still receive multicast commits / remote arrivals
   if (warp == W_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -789,19 +920,35 @@ bool pick_inst(int d, int k, Inst* out) {
   return true;
 }
 
-template <int KP, int DP>
+template <int KP, int DP, bool PAIR>
 int launch_inst(b2k_ctx* ctx, int grid, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml,
                 const FusedArgs& a, cudaStream_t s) {
-  using G = Cfg<KP, DP>;
-  auto kern = k_fused_assign_update<KP, DP>;
+  using G = Cfg<KP, DP, PAIR>;
+  auto kern = k_fused_assign_update<KP, DP, PAIR>;
   B2K_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-  kern<<<grid, NTHREADS, G::SMEM_BYTES, s>>>(mx, mh, ml, a);
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = G::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // the CTA pair of tcgen05 cta_group::2
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2K_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, mx, mh, ml, a));
+  } else {
+    kern<<<grid, NTHREADS, G::SMEM_BYTES, s>>>(mx, mh, ml, a);
+  }
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
 }
 
 struct PlanLayout {
-  size_t off_chi, off_clo, off_cnorm, off_partials, off_counts, off_cost, total;
+  size_t off_chi, off_clo, off_cnorm, off_tab, off_partials, off_counts, off_cost, total;
 };
 PlanLayout plan_layout(const B2kFusedPlan& p, int k, int d) {
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -810,6 +957,7 @@ PlanLayout plan_layout(const B2kFusedPlan& p, int k, int d) {
   L.off_chi = o; o = al(o + (size_t)p.KP * p.DP * 4);
   L.off_clo = o; o = al(o + (size_t)p.KP * p.DP * 4);
   L.off_cnorm = o; o = al(o + (size_t)p.KP * 4);
+  L.off_tab = o; o = al(o + 512);
   L.off_partials = o; o = al(o + (size_t)p.grid * k * d * 4);
   L.off_counts = o; o = al(o + (size_t)p.grid * k * 4);
   L.off_cost = o; o = al(o + (size_t)p.grid * 8);
@@ -835,8 +983,16 @@ int b2k_fused_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan) {
   int64_t ntiles = (n + TM - 1) / TM;
   int grid = ctx->sm_count;
   if (ctx->grid_limit > 0 && ctx->grid_limit < grid) grid = ctx->grid_limit;
-  if (ntiles < grid) grid = (int)ntiles;
-  if (grid < 1) grid = 1;
+  plan->pair = (ctx->pair != 0 && in.KP == 64 && in.DP == 128) ? 1 : 0;
+  if (plan->pair) {
+    int64_t npairs = (ntiles + 1) / 2;
+    grid &= ~1;
+    if (npairs * 2 < grid) grid = (int)npairs * 2;
+    if (grid < 2) grid = 2;
+  } else {
+    if (ntiles < grid) grid = (int)ntiles;
+    if (grid < 1) grid = 1;
+  }
   plan->grid = grid;
   plan->scratch_bytes = plan_layout(*plan, k, d).total;
   return B2K_OK;
@@ -853,7 +1009,7 @@ void b2k_fused_views(const B2kFusedPlan& plan, void* plan_scratch, int k, int d,
 
 int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d,
                      const float* C, int k, int32_t* labels_out, float* mindist_out, bool do_update,
-                     const B2kLoopState* st, cudaStream_t s) {
+                     const B2kLoopState* st, cudaStream_t s, const double* prev_counts) {
   PlanLayout L = plan_layout(plan, k, d);
   char* b = static_cast<char*>(plan_scratch);
   float* Chi = reinterpret_cast<float*>(b + L.off_chi);
@@ -861,16 +1017,19 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   float* cnorm = reinterpret_cast<float*>(b + L.off_cnorm);
 
   k_prep_centers_tc<<<(plan.KP * 32 + 255) / 256, 256, 0, s>>>(C, k, d, plan.KP, plan.DP, Chi, Clo, cnorm, st);
-  ctx->stats.kernel_launches++;
+  uint8_t* keytab = reinterpret_cast<uint8_t*>(b + L.off_tab);
+  k_balance_table<<<1, 128, 0, s>>>(do_update ? prev_counts : nullptr, k, plan.KP, keytab, keytab + 256, st);
+  ctx->stats.kernel_launches += 2;
   B2K_CUDA_OK(ctx, cudaGetLastError());
 
   CUtensorMap mx, mh, ml;
   B2K_TRY(encode_2d(ctx, &mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)d * 4, CHUNK, TM,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-  B2K_TRY(encode_2d(ctx, &mh, Chi, (uint64_t)plan.DP, (uint64_t)plan.KP, (uint64_t)plan.DP * 4, CHUNK,
-                    (uint32_t)plan.KP, CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
-  B2K_TRY(encode_2d(ctx, &ml, Clo, (uint64_t)plan.DP, (uint64_t)plan.KP, (uint64_t)plan.DP * 4, CHUNK,
-                    (uint32_t)plan.KP, CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  const uint32_t cbox = (uint32_t)(plan.pair ? plan.KP / 2 : plan.KP);   // centre rows each CTA keeps in smem
+  B2K_TRY(encode_2d(ctx, &mh, Chi, (uint64_t)plan.DP, (uint64_t)plan.KP, (uint64_t)plan.DP * 4, CHUNK, cbox,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  B2K_TRY(encode_2d(ctx, &ml, Clo, (uint64_t)plan.DP, (uint64_t)plan.KP, (uint64_t)plan.DP * 4, CHUNK, cbox,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
 
   FusedArgs a{};
   a.n = n;
@@ -878,6 +1037,8 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.k = k;
   a.d = d;
   a.cnorm = cnorm;
+  a.keytab = keytab;
+  a.keyinv = keytab + 256;
   a.partials = reinterpret_cast<float*>(b + L.off_partials);
   a.counts = reinterpret_cast<int32_t*>(b + L.off_counts);
   a.cost_partials = reinterpret_cast<double*>(b + L.off_cost);
@@ -897,7 +1058,8 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
 
   int rc = B2K_ERR_UNSUPPORTED;
 #define B2K_DISPATCH(KP_, DP_) \
-  if (plan.KP == KP_ && plan.DP == DP_) rc = launch_inst<KP_, DP_>(ctx, plan.grid, mx, mh, ml, a, s);
+  if (!plan.pair && plan.KP == KP_ && plan.DP == DP_) rc = launch_inst<KP_, DP_, false>(ctx, plan.grid, mx, mh, ml, a, s);
+  if (plan.pair && plan.KP == 64 && plan.DP == 128) rc = launch_inst<64, 128, true>(ctx, plan.grid, mx, mh, ml, a, s);
   B2K_DISPATCH(64, 128)
   B2K_DISPATCH(64, 64)
   B2K_DISPATCH(64, 32)

@@ -38,6 +38,7 @@ struct b2k_ctx {
   int check_every = 4;
   int grid_limit = 0;
   int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
+  int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
   int profile_fused = 0;         // record per-role blocked-cycle counters of the fused kernel
   long long* prof_dev = nullptr;  // [grid][18 warps][8]
   int prof_grid = 0;
@@ -124,6 +125,7 @@ int b2k_launch_histogram(b2k_ctx* ctx, const int32_t* labels, int64_t n, int m, 
 struct B2kFusedPlan {
   int KP = 0, DP = 0;        // padded cluster count / dimension of the instantiation, 0 = unsupported
   int grid = 0;              // persistent CTAs
+  int pair = 0;              // 1: CTA-pair (tcgen05 cta_group::2) instantiation, grid is even
   size_t scratch_bytes = 0;  // Chi/Clo/cnorm + partials/counts/cost
 };
 bool b2k_fused_supported(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X);
@@ -132,7 +134,7 @@ int b2k_fused_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan);
 // `do_update` = accumulate partial sums (Lloyd iteration) or labels only (assign/inertia pass).
 int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X,
                      int64_t n, int d, const float* C, int k, int32_t* labels_out, float* mindist_out,
-                     bool do_update, const B2kLoopState* st, cudaStream_t s);
+                     bool do_update, const B2kLoopState* st, cudaStream_t s, const double* prev_counts = nullptr);
 // Views into the plan scratch after a fused pass (to feed b2k_launch_reduce_partials)
 void b2k_fused_views(const B2kFusedPlan& plan, void* plan_scratch, int k, int d, float** partials,
                      int32_t** counts, double** cost_partials);

@@ -5,6 +5,7 @@ import numpy as np, torch
 from spark_rapids_ml_b200 import _native
 n, d, k = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000, 128, 64
 ctx = _native.Context(0)
+if len(sys.argv) > 2: ctx.set_option("pair", int(sys.argv[2]))
 g = torch.Generator(device="cuda").manual_seed(1)
 ctr = torch.rand((k, d), generator=g, device="cuda") * 20 - 10
 X = torch.empty((n, d), device="cuda")
@@ -36,3 +37,7 @@ for r, ws in roles.items():
         per_warp = (sub[:, :, 0] - sub[:, :, 1] - sub[:, :, 2]).mean(axis=0) / tiles_per_cta
         line += "  busy/warp=" + ",".join(f"{v:.0f}" for v in per_warp)
     print(line)
+    if len(sys.argv) > 2 and r in ("convert","mma","epilogue"):
+        for par in (0,1):
+            sp = P[par::2][:, list(ws), :]
+            print("      rank", par, "role", int(sp[:,:,0].mean()/tiles_per_cta), "blocked", [int(sp[:,:,1+i].mean()/tiles_per_cta) for i in range(3)])
