@@ -395,17 +395,17 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     tma_prefetch_desc(&mapClo);
     for (int i = 0; i < G::NSLOT; ++i) {
       mbar_init(bar(G::B_XFULL + i), 1);
-      mbar_init(bar(G::B_XEMPTY + i), 4 + N_UPD);
+      mbar_init(bar(G::B_XEMPTY + i), 2);                 // convert role + update role
     }
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar(G::B_AFULL + i), PAIR ? 8 : 4);       // PAIR: the convert warps of BOTH CTAs feed the leader
+      mbar_init(bar(G::B_AFULL + i), PAIR ? 2 : 1);       // PAIR: the convert roles of BOTH CTAs feed the leader
       mbar_init(bar(G::B_AEMPTY + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(G::B_DFULL + i), 1);
-      mbar_init(bar(G::B_DEMPTY + i), PAIR ? 8 : 4);
-      mbar_init(bar(G::B_LFULL + i), 4);
-      mbar_init(bar(G::B_LEMPTY + i), N_UPD);
+      mbar_init(bar(G::B_DEMPTY + i), PAIR ? 2 : 1);
+      mbar_init(bar(G::B_LFULL + i), 1);
+      mbar_init(bar(G::B_LEMPTY + i), 1);
       mbar_init(bar(G::B_NFULL + i), 4);
       mbar_init(bar(G::B_NEMPTY + i), 4);
     }
@@ -578,8 +578,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tmem_st_x32(a_addr + CHUNK, lo);
         tmem_wait_st();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
+        asm volatile("bar.sync 3, 128;" ::: "memory");   // the 4 convert warps (hardware barrier: no polling)
+        if (warp == W_CONVERT0 && lane == 0) {            // one arrival per role keeps the waiters' wake-ups low
           if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_AFULL + as), 0u);
           else mbar_arrive(bar(G::B_AFULL + as));
           mbar_arrive(bar(G::B_XEMPTY + xs));
@@ -644,11 +644,6 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {   // D buffer may be overwritten by tile ti+2
-        if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_DEMPTY + b), 0u);
-        else mbar_arrive(bar(G::B_DEMPTY + b));
-      }
 
       const int64_t grow = (int64_t)tile * TM + r;
       const bool valid = grow < args.n;
@@ -664,6 +659,10 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const int rank = __popc(same & ((1u << lane) - 1u));
       if (valid && rank == 0) cnt[q * 128 + key] = (uint8_t)__popc(same);
       asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+      if (warp == W_EPI0 && lane == 0) {   // all four have drained D: it may be overwritten by tile ti+2
+        if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_DEMPTY + b), 0u);
+        else mbar_arrive(bar(G::B_DEMPTY + b));
+      }
       int tot[G::KPL];
       int lane_sum = 0;
 #pragma unroll
@@ -704,8 +703,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         if (lane == 31) start[KP] = (uint8_t)incl;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(G::B_LFULL + b));
+      asm volatile("bar.sync 4, 128;" ::: "memory");      // row list complete
+      if (warp == W_EPI0 && lane == 0) mbar_arrive(bar(G::B_LFULL + b));
       // off the critical path: outputs and cost
       if (valid && args.labels_out) args.labels_out[grow] = bj;
       if (need_cost) {
@@ -806,8 +805,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");     // the 8 update warps
+      if (warp == W_UPD0 && lane == 0) {
         mbar_arrive(bar(G::B_LEMPTY + b));
         int s2 = xs;
 #pragma unroll
