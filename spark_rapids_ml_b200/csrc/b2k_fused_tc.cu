@@ -354,6 +354,7 @@ struct FusedArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int do_update;
+  int pf_dist;             // L2 prefetch look-ahead in tiles (-1 = off)
   int probe;               // EXPERIMENT 3: update warps ignore lab_full/lab_empty (stale row lists; WRONG sums)
   int need_cost;           // compute ||x||^2, min distance and the cost partial (assign / inertia passes)
   const B2kLoopState* st;
@@ -459,8 +460,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __syncwarp();
     int xs = 0;
     uint32_t xph = 0;
-    constexpr int PF = 3;   // tiles of L2 look-ahead beyond what the ring already holds
-    if (elect_one()) {
+    const int PF = args.pf_dist;   // tiles of L2 look-ahead beyond what the ring already holds (< 0: no prefetch)
+    if (PF >= 0 && elect_one()) {
       for (int p = 0; p < PF + 2; ++p) {
         const int pt = tile_of(p);
         if (p < nit && pt < args.ntiles)
@@ -470,7 +471,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __syncwarp();
     for (int ti = 0; ti < nit; ++ti) {
       const int tile = tile_of(ti);
-      if (elect_one()) {
+      if (PF >= 0 && elect_one()) {
         const int pt = tile_of(ti + PF + 2);
         if (ti + PF + 2 < nit && pt < args.ntiles)
           for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
@@ -1044,6 +1045,7 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.labels_out = labels_out;
   a.mind_out = mindist_out;
   a.do_update = do_update ? 1 : 0;
+  a.pf_dist = ctx->pf_dist;
   a.probe = ctx->probe;
   a.need_cost = (!do_update || mindist_out != nullptr) ? 1 : 0;
   a.st = st;
