@@ -37,12 +37,12 @@ constexpr int TMEM_COLS = 512;
 
 constexpr int W_CONVERT0 = 0;      // warps 0-3  (lane quadrant = warp % 4)
 constexpr int W_EPI0 = 4;          // warps 4-7
-constexpr int W_UPD0 = 8;          // warps 8-15
-constexpr int W_TMA = 16;
-constexpr int W_MMA = 17;
-constexpr int NWARPS = 18;
+constexpr int W_UPD0 = 8;          // warps 8-23: 16 update warps
+constexpr int N_UPD = 16;
+constexpr int W_TMA = W_UPD0 + N_UPD;   // 24
+constexpr int W_MMA = W_TMA + 1;        // 25
+constexpr int NWARPS = 26;              // 832 threads -> 72 registers per thread
 constexpr int NTHREADS = NWARPS * 32;
-constexpr int N_UPD = 8;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
@@ -200,6 +200,14 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -551,42 +559,63 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       float xn = 0.f;
+      // chunks are converted in groups of CG: one tcgen05.wait::st / hardware barrier / signal per group
+      constexpr int CG = (G::NCH % 2 == 0) ? 2 : 1;
 #pragma unroll 1
-      for (int c = 0; c < G::NCH; ++c) {
-        mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
-        mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
+      for (int c = 0; c < G::NCH; c += CG) {
+        int xs_g[CG], as_g[CG];
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          xs_g[g] = xs;
+          as_g[g] = as;
+          mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
+          mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
+          if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
+          if (++as == NA) { as = 0; aph ^= 1u; }
+        }
         tc_fence_after();
-        const uint32_t rowaddr = ring + xs * SLOT_BYTES + (uint32_t)r * 128u;
-        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = lds128(rowaddr + (((uint32_t)j ^ swz) << 4));
-          float e[4] = {v.x, v.y, v.z, v.w};
+        for (int g = 0; g < CG; ++g) {
+          const uint32_t rowaddr = ring + xs_g[g] * SLOT_BYTES + (uint32_t)r * 128u;
+          const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(as_g[g] * A_COLS);
+          // halves of 16 columns: bounds the live registers (the CTA runs 26 warps at 72 registers/thread)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            // The tensor core TRUNCATES fp32 operands to tf32 (tools/probe_trunc.py), so adding half a tf32 ulp
-            // to the stored bits makes the hardware's truncation a round-to-nearest: no explicit mask needed on
-            // the stored words; only the value used to form `lo` is masked.
-            const uint32_t hs = __float_as_uint(e[t]) + 0x1000u;
-            const float l = e[t] - __uint_as_float(hs & 0xffffe000u);   // exact
-            hi[j * 4 + t] = hs;
-            lo[j * 4 + t] = __float_as_uint(l) + 0x1000u;
-            if (need_cost) xn = fmaf(e[t], e[t], xn);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              const int j = h * 4 + j2;
+              float4 v = lds128(rowaddr + (((uint32_t)j ^ swz) << 4));
+              float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                // The tensor core TRUNCATES fp32 operands to tf32 (measured: tools/probe_trunc.py).  hi is stored
+                // as the raw fp32 word (the hardware takes its top 19 bits: hi = trunc_tf32(x), zero ALU work),
+                // lo = x - trunc_tf32(x) is exact, and adding half a tf32 ulp to lo's stored bits turns the
+                // hardware truncation of lo into a round-to-nearest (unbiased).
+                // x.c = hi.c_hi + lo.c_hi + hi.c_lo + O(2^-22 |x||c|).
+                const uint32_t xb = __float_as_uint(e[t]);
+                const float l = e[t] - __uint_as_float(xb & 0xffffe000u);
+                hi[j2 * 4 + t] = xb;
+                lo[j2 * 4 + t] = __float_as_uint(l) + 0x1000u;
+                if (need_cost) xn = fmaf(e[t], e[t], xn);
+              }
+            }
+            tmem_st_x16(a_addr + h * 16, hi);
+            tmem_st_x16(a_addr + CHUNK + h * 16, lo);
           }
         }
-        const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(as * A_COLS);
-        tmem_st_x32(a_addr, hi);
-        tmem_st_x32(a_addr + CHUNK, lo);
         tmem_wait_st();
         tc_fence_before();
         asm volatile("bar.sync 3, 128;" ::: "memory");   // the 4 convert warps (hardware barrier: no polling)
         if (warp == W_CONVERT0 && lane == 0) {            // one arrival per role keeps the waiters' wake-ups low
-          if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_AFULL + as), 0u);
-          else mbar_arrive(bar(G::B_AFULL + as));
-          mbar_arrive(bar(G::B_XEMPTY + xs));
+#pragma unroll
+          for (int g = 0; g < CG; ++g) {
+            if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_AFULL + as_g[g]), 0u);
+            else mbar_arrive(bar(G::B_AFULL + as_g[g]));
+            mbar_arrive(bar(G::B_XEMPTY + xs_g[g]));
+          }
         }
-        if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
-        if (++as == NA) { as = 0; aph ^= 1u; }
       }
       if (need_cost) {
         mbar_wait_p(bar(G::B_NEMPTY + b), bph ^ 1u, prof, pw[2]);
@@ -806,7 +835,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           }
         }
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");     // the 8 update warps
+      asm volatile("bar.sync 2, 512;" ::: "memory");     // the 16 update warps
       if (warp == W_UPD0 && lane == 0) {
         mbar_arrive(bar(G::B_LEMPTY + b));
         int s2 = xs;

@@ -17,7 +17,7 @@ ctx.kmeans_lloyd(X, C, 3, -1.0)
 ctx.set_option("profile_fused", 1)
 ctx.kmeans_lloyd(X, C, 1, -1.0)
 P = ctx.fused_profile().astype(np.float64)
-roles = {"convert": range(0, 4), "epilogue": range(4, 8), "update": range(8, 16), "tma": [16], "mma": [17]}
+roles = {"convert": range(0, 4), "epilogue": range(4, 8), "update": range(8, 24), "tma": [24], "mma": [25]}
 names = {"convert": ["x_full", "a_empty", "xn_empty"], "epilogue": ["d_full", "xn_full", "lab_empty"],
          "update": ["lab_full", "x_full"], "tma": ["x_empty"], "mma": ["d_empty", "a_full"]}
 ntiles = (n + 127) // 128
