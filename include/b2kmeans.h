@@ -112,6 +112,9 @@ int b2k_get_stats(const b2k_ctx* ctx, b2k_stats* out);
  * layout [grid][warps][8] = {role cycles, blocked cycles on up to 6 barrier kinds, 0}. Synchronises the device. */
 int b2k_get_fused_profile(b2k_ctx* ctx, long long* out, int64_t cap, int* grid_out, int* warps_out);
 int b2k_reset_stats(b2k_ctx* ctx);
+/* Diagnostics: one pass of X[n, d] (d % 32 == 0) through an nslot x 16 KB TMA ring whose slots are released
+ * `hold_cycles` after landing; *out_ms = device time.  Maps the bandwidth ceiling of the fused kernel's ring. */
+int b2k_debug_tma_stream(b2k_ctx* ctx, const float* X, int64_t n, int d, int nslot, int hold_cycles, float* out_ms);
 
 /* ---- communicator (NCCL over NVLink; one rank per process per GPU) ---- */
 int b2k_comm_unique_id(char out[B2K_UNIQUE_ID_BYTES]); /* rank 0 only */

@@ -1121,3 +1121,93 @@ extern "C" int b2k_get_fused_profile(b2k_ctx* ctx, long long* out, int64_t cap, 
   if (warps_out) *warps_out = NWARPS;
   return B2K_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics: TMA streaming microbenchmark.  Persistent CTAs pull X through an nslot x 16 KB shared-memory
+// ring with the same 128B-swizzled [128 x 32 f32] boxes as the fused kernel; one consumer warp releases every
+// slot `hold` clock cycles after it lands.  Gives the bandwidth the ring can sustain as a function of its depth
+// and of how long the pipeline holds a slot (the fused kernel's ceiling).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(1024, 1) k_tma_stream(const __grid_constant__ CUtensorMap mapX, int ntiles, int nch,
+                                                      int nslot, int hold, unsigned long long* sink) {
+  extern __shared__ uint8_t smem_raw2[];
+  const uint32_t base = (smem_u32(smem_raw2) + 1023u) & ~1023u;
+  const uint32_t bars = base + (uint32_t)nslot * SLOT_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nslot; ++i) {
+      mbar_init(bars + 8u * i, 1);
+      mbar_init(bars + 8u * (nslot + i), 1);
+    }
+    mbar_init(bars + 8u * (2 * nslot), 1);        // "never" barrier: extra warps poll it (polling-load experiment)
+    *reinterpret_cast<volatile int*>(smem_raw2 + (base - smem_u32(smem_raw2)) + nslot * SLOT_BYTES + 8 * (2 * nslot + 2)) = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  volatile int* stop = reinterpret_cast<volatile int*>(smem_raw2 + (base - smem_u32(smem_raw2)) + nslot * SLOT_BYTES + 8 * (2 * nslot + 2));
+  int s = 0;
+  uint32_t ph = 0;
+  if (warp >= 2) {                                 // spinner warps
+    while (*stop == 0) { mbar_try_wait(bars + 8u * (2 * nslot), 0); }
+    return;
+  }
+  if (warp == 0) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int c = 0; c < nch; ++c) {
+        mbar_wait(bars + 8u * (nslot + s), ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(bars + 8u * s, SLOT_BYTES);
+          tma_load_2d(base + s * SLOT_BYTES, &mapX, bars + 8u * s, c * CHUNK, tile * TM);
+        }
+        __syncwarp();
+        if (++s == nslot) { s = 0; ph ^= 1u; }
+      }
+  } else {
+    unsigned long long acc = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int c = 0; c < nch; ++c) {
+        mbar_wait(bars + 8u * s, ph);
+        if (hold > 0) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < hold) {}
+        }
+        acc += lane;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8u * (nslot + s));
+        if (++s == nslot) { s = 0; ph ^= 1u; }
+      }
+    if (acc == 0xdeadbeefULL) sink[0] = acc;
+    *stop = 1;
+  }
+}
+}  // namespace
+
+// out_ms receives the device time of one pass over X[n, d] (d multiple of 32) with the given ring depth / hold
+extern "C" int b2k_debug_tma_stream(b2k_ctx* ctx, const float* X, int64_t n, int d, int nslot, int hold_cycles,
+                                    float* out_ms) {
+  const int spinners = hold_cycles < 0 ? -hold_cycles : 0;   // hold < 0: |hold| extra warps polling an mbarrier
+  if (hold_cycles < 0) hold_cycles = 0;
+  if (!ctx || !X || !out_ms || d % CHUNK != 0 || nslot < 1 || nslot > 13)
+    return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_debug_tma_stream: bad argument");
+  CUtensorMap mx;
+  B2K_TRY(encode_2d(ctx, &mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)d * 4, CHUNK, TM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  const int smem = nslot * SLOT_BYTES + 2 * nslot * 8 + 1024 + 128;
+  B2K_CUDA_OK(ctx, cudaFuncSetAttribute(k_tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B2K_TRY(b2k_scratch_reserve(ctx, 4096));
+  cudaEvent_t e0, e1;
+  B2K_CUDA_OK(ctx, cudaEventCreate(&e0));
+  B2K_CUDA_OK(ctx, cudaEventCreate(&e1));
+  const int ntiles = (int)((n + TM - 1) / TM);
+  for (int rep = 0; rep < 2; ++rep) {
+    if (rep == 1) B2K_CUDA_OK(ctx, cudaEventRecord(e0, 0));
+    k_tma_stream<<<ctx->sm_count, 64 + 32 * spinners, smem, 0>>>(mx, ntiles, d / CHUNK, nslot, hold_cycles,
+                                                 static_cast<unsigned long long*>(ctx->scratch));
+  }
+  B2K_CUDA_OK(ctx, cudaEventRecord(e1, 0));
+  B2K_CUDA_OK(ctx, cudaEventSynchronize(e1));
+  B2K_CUDA_OK(ctx, cudaEventElapsedTime(out_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return B2K_OK;
+}

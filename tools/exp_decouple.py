@@ -10,7 +10,7 @@ X = torch.empty((n, d), device="cuda")
 for s in range(0, n, 1_000_000):
     e = min(n, s + 1_000_000)
     X[s:e] = ctr[torch.randint(0, k, (e - s,), generator=g, device="cuda")] + torch.randn((e - s, d), generator=g, device="cuda")
-for probe in (0, 3):
+for probe in (0, 4):
     ctx.set_option("probe", probe)
     C = X[:k].clone()
     ctx.kmeans_lloyd(X, C, 3, -1.0)
@@ -23,6 +23,6 @@ ctx.kmeans_lloyd(X, C, 1, -1.0)
 import numpy as np
 P = ctx.fused_profile().astype(np.float64)
 tpc = ((n + 127) // 128) / P.shape[0]
-for nm, ws in {"convert": range(0, 4), "epilogue": range(4, 8), "update": range(8, 16), "tma": [16], "mma": [17]}.items():
+for nm, ws in {"convert": range(0, 4), "epilogue": range(4, 8), "update": range(8, 24), "tma": [24], "mma": [25]}.items():
     sub = P[:, list(ws), :]
     print(nm, "role", int(sub[:, :, 0].mean() / tpc), "blocked", [int(sub[:, :, 1 + i].mean() / tpc) for i in range(3)])
