@@ -589,14 +589,15 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
               float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                // The tensor core TRUNCATES fp32 operands to tf32 (measured: tools/probe_trunc.py).  hi is stored
-                // as the raw fp32 word (the hardware takes its top 19 bits: hi = trunc_tf32(x), zero ALU work),
-                // lo = x - trunc_tf32(x) is exact, and adding half a tf32 ulp to lo's stored bits turns the
-                // hardware truncation of lo into a round-to-nearest (unbiased).
-                // x.c = hi.c_hi + lo.c_hi + hi.c_lo + O(2^-22 |x||c|).
-                const uint32_t xb = __float_as_uint(e[t]);
-                const float l = e[t] - __uint_as_float(xb & 0xffffe000u);
-                hi[j2 * 4 + t] = xb;
+                // The tensor core TRUNCATES fp32 operands to tf32 (measured: tools/probe_trunc.py).  Adding half a
+                // tf32 ulp to the stored word turns that truncation into round-to-nearest, for hi and for lo:
+                //   hi = RN_tf32(x)  (|x - hi| <= 2^-12 |x|),  lo = RN_tf32(x - hi)  (x - hi is exact in fp32)
+                // so x.c = hi.c_hi + lo.c_hi + hi.c_lo + O(2^-23 |x||c|): fp32-class accuracy from three tf32 MMAs.
+                // (Storing hi un-rounded saves one ALU op per element but doubles the residual; a golden-fixture row
+                // with a 3e-7 relative margin then flips, so the rounding stays.)
+                const uint32_t hs = __float_as_uint(e[t]) + 0x1000u;
+                const float l = e[t] - __uint_as_float(hs & 0xffffe000u);   // exact
+                hi[j2 * 4 + t] = hs;
                 lo[j2 * 4 + t] = __float_as_uint(l) + 0x1000u;
                 if (need_cost) xn = fmaf(e[t], e[t], xn);
               }
