@@ -770,7 +770,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int ti = 0; ti < nit; ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      if (args.probe != 3) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
+      // one warp polls the mbarrier, the other 15 park in a hardware barrier (no issue slots, no wake-ups)
+      if (warp == W_UPD0 && args.probe != 3) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
+      asm volatile("bar.sync 7, 512;" ::: "memory");
       // slots of this tile's chunks.  Their x_full phases completed before the convert warps consumed them, which
       // happens-before the MMA commit, the epilogue and hence this tile's lab_full: no need to poll them again.
       uint32_t slot_addr[G::NCH];
