@@ -568,11 +568,14 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         for (int g = 0; g < CG; ++g) {
           xs_g[g] = xs;
           as_g[g] = as;
-          mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
-          mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
+          if (warp == W_CONVERT0) {
+            mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
+            mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
+          }
           if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
           if (++as == NA) { as = 0; aph ^= 1u; }
         }
+        asm volatile("bar.sync 6, 128;" ::: "memory");
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
@@ -635,7 +638,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const int tile = tile_of(ti);
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
+      if (warp == W_EPI0) mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
+      asm volatile("bar.sync 5, 128;" ::: "memory");
       tc_fence_after();
       float best = __int_as_float(0x7f800000);
       int bj = 0;
