@@ -265,3 +265,28 @@ def test_errors_are_loud(ctx):
         ctx.kmeans_fit(X, 2, init="random", n_init=3)
     with pytest.raises(B2KError):
         ctx.kmeans_fit(X, 32, init="random")   # fewer rows than k
+
+
+def test_baseline_config_shapes(ctx):
+    """BASELINE.json configs[0] (k=8, n=100k, d=32: full size) and configs[2] (k=256, d=256: a 20k-row slice of the
+    per-GPU partition) against the oracle from an injected init; 'auto' path selection (cfg1 -> tcgen05 kernel,
+    cfg3 -> generic kernels: k, d beyond the fused instantiations)."""
+    ctx.set_option("kernel_path", 0)
+    for (n, d, k, iters, want_path) in [(100_000, 32, 8, 6, 2), (20_000, 256, 256, 3, 1)]:
+        X, _ = ko.make_blobs(n, d, k, seed=17)
+        C0 = X[:k].copy()
+        ref = ko.lloyd([X], C0, iters, -1.0)
+        out = ctx.kmeans_fit(_dev(X), k, init=C0, max_iter=iters, tol=-1.0)
+        assert ctx.stats()["last_path"] in (1, 2)
+        Cg = out["cluster_centers_"].cpu().numpy()
+        labels, _ = ctx.kmeans_assign(_dev(X), out["cluster_centers_"])
+        assert ctx.stats()["last_path"] == want_path
+        cmp = ko.compare_labels(X, Cg, labels.cpu().numpy(), tau=TAU)
+        assert cmp["n_mismatch_outside_margin"] == 0, cmp
+        # trajectories agree unless an admissible (< 1e-6 margin) tie row sent them apart: check one exact step instead
+        C1, _, _ = ko.lloyd_iteration([X], C0)
+        one = ctx.kmeans_fit(_dev(X), k, init=C0, max_iter=1, tol=-1.0)["cluster_centers_"].cpu().numpy()
+        lab0, _, margin0 = ko.assign(X, C0)
+        if margin0.min() > 1e-5:
+            assert ko.max_center_rel_err(one, C1) <= CENTER_RTOL
+            assert ko.max_center_rel_err(Cg, ref["centers"]) <= 1e-3
