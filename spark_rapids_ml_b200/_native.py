@@ -14,7 +14,8 @@ from typing import Any, Dict, Optional, Sequence, Tuple
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libb2kmeans.so")
+# B2K_LIB selects another build of the same library (e.g. the diagnostic libb2kmeans_trace.so from `make trace`)
+LIB_PATH = os.environ.get("B2K_LIB") or os.path.join(_PKG_DIR, "libb2kmeans.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 B2K_OK = 0

@@ -20,6 +20,8 @@
 #include <float.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "b2k_internal.cuh"
 
 namespace {
@@ -27,6 +29,29 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // configuration
 // ------------------------------------------------------------------------------------------------
+// Diagnostic build (make trace -> libb2kmeans_trace.so): per-stage cycle counters and a per-tile event trace on top of
+// the blocked-cycle counters of option "profile_fused".  Off in the product build: even the predicated-off timer
+// reads cost ~10 % of the kernel's speed (register pressure in the convert / epilogue loops; measured).
+#ifndef B2K_TRACE
+#define B2K_TRACE 0
+#endif
+#if B2K_TRACE
+#define B2K_T0(v) const long long v = prof ? clock64() : 0
+#define B2K_TACC(slot, expr) do { if (prof) pw[slot] += (expr); } while (0)
+#define B2K_TR(ti, ev) tr(ti, ev)
+#define B2K_TRACE_CTAS 4
+#else
+#define B2K_T0(v) ((void)0)
+#define B2K_TACC(slot, expr) ((void)0)
+#define B2K_TR(ti, ev) ((void)0)
+#define B2K_TRACE_CTAS 0
+#endif
+#ifndef B2K_PACKED_SPLIT
+#define B2K_PACKED_SPLIT 1
+#endif
+#ifndef B2K_NSLOT_CAP
+#define B2K_NSLOT_CAP 12
+#endif
 constexpr int TM = 128;            // rows per tile (UMMA M)
 constexpr int CHUNK = 32;          // f32 per 128-byte swizzle row = one TMA box / K chunk
 constexpr int SLOT_BYTES = TM * CHUNK * 4;  // 16 KB
@@ -45,6 +70,14 @@ constexpr int NWARPS = 26;              // 832 threads -> 72 registers per threa
 constexpr int NTHREADS = NWARPS * 32;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
+// counting-sort scratch (epilogue -> update hand-off), byte offsets inside it:
+//   [0, 1024)      per-warp key histograms, parity buffered: u8 [2][4][128]
+//   [1024, 1536)   sorted row list, double buffered: u16 [2][128]; an entry is the row's byte offset inside a ring
+//                  slot with its swizzle phase folded in: row * 128 + ((row & 7) << 4)
+//   [1536, 1920)   exclusive start offset per sort key, double buffered: u8 [2][192]
+//   [1920, 2048)   keytab u8 [128]      [2048, 2176)   keyinv u8 [128]
+constexpr int SORT_BYTES = 2304;
+constexpr int SORT_ROWS = 1024, SORT_START = 1536, SORT_KEYTAB = 1920, SORT_KEYINV = 2048;
 
 template <int KP, int DP, bool PAIR = false>
 struct Cfg {
@@ -56,9 +89,9 @@ struct Cfg {
   static_assert(DP % CHUNK == 0 && DP >= CHUNK && DP <= 256, "DP");
   static constexpr int NCH = DP / CHUNK;
   static constexpr int C_BYTES = KPS * DP * 4;                 // one of Chi / Clo (this CTA's share)
-  static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64 + 2048 /*sort*/;
+  static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64 + SORT_BYTES;
   static constexpr int NSLOT_RAW = (int)((SMEM_LIMIT - 1024 - 2 * C_BYTES - MISC) / SLOT_BYTES);
-  static constexpr int NSLOT = NSLOT_RAW > 12 ? 12 : NSLOT_RAW;
+  static constexpr int NSLOT = NSLOT_RAW > B2K_NSLOT_CAP ? B2K_NSLOT_CAP : NSLOT_RAW;
   static_assert(NSLOT >= NCH + 1, "ring too small");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_CHI = NSLOT * SLOT_BYTES;
@@ -83,7 +116,7 @@ struct Cfg {
   static_assert(NBARS * 8 <= 512, "barrier area");
   static constexpr int OFF_TMEMPTR = OFF_BARS + 512;
   static constexpr int OFF_SORT = OFF_TMEMPTR + 64;            // counting-sort scratch (epilogue -> update)
-  static constexpr int SMEM_BYTES = OFF_SORT + 2048 + 1024;   // +1024: manual 1 KB alignment slack
+  static constexpr int SMEM_BYTES = OFF_SORT + SORT_BYTES + 1024;   // +1024: manual 1 KB alignment slack
   static_assert(SMEM_BYTES <= (int)SMEM_LIMIT, "smem");
   static constexpr int UPL = (DP / 4 + 31) / 32;   // float4 units per lane in the update warps
   static constexpr int CPW = (KP + N_UPD - 1) / N_UPD;  // clusters per update warp
@@ -125,8 +158,12 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 22)) mbar_timeout(bar, parity);
+  for (;;) {   // 4 polls per bookkeeping step: the poll loop is 2 instructions per try
+    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
+    if (++spins == (1u << 20)) mbar_timeout(bar, parity);
   }
 }
 
@@ -217,6 +254,40 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two fp32 operations per issue slot)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+__device__ __forceinline__ void lds128_2(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 
 // round-to-nearest (ties away) fp32 -> tf32 (10 explicit mantissa bits), result has the low 13 bits clear
@@ -396,6 +467,13 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   const bool need_cost = args.need_cost != 0;
   long long pw[6] = {0, 0, 0, 0, 0, 0};   // blocked cycles per barrier kind (role specific)
   const long long t_role0 = prof ? clock64() : 0;
+#if B2K_TRACE
+  // event trace of 16 consecutive tiles (200..215) for CTAs 0 and 1, stored behind the per-warp counters
+  long long* trace = (prof && blockIdx.x < 2) ? args.prof + (size_t)gridDim.x * NWARPS * 8 + blockIdx.x * 256 : nullptr;
+  auto tr = [&](int ti, int ev) {
+    if (trace != nullptr && ti >= 200 && ti < 216 && (threadIdx.x & 31) == 0) trace[(ti - 200) * 16 + ev] = clock64();
+  };
+#endif
 
   // ---- one-time setup ----
   if (warp == W_TMA && lane == 0) {
@@ -435,8 +513,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     }
   }
   for (int j = threadIdx.x; j < KP; j += NTHREADS) cnorm_s[j] = args.cnorm[j];
-  uint8_t* keytab_s = sort_s + 1792;   // [KP]
-  uint8_t* keyinv_s = sort_s + 1920;   // [KP]
+  uint8_t* keytab_s = sort_s + SORT_KEYTAB;   // [KP]
+  uint8_t* keyinv_s = sort_s + SORT_KEYINV;   // [KP]
   for (int j = threadIdx.x; j < KP; j += NTHREADS) { keytab_s[j] = args.keytab[j]; keyinv_s[j] = args.keyinv[j]; }
   tc_fence_before();
   __syncthreads();
@@ -493,6 +571,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           tma_load_2d(ring + xs * SLOT_BYTES, &mapX, bar(G::B_XFULL + xs), c * CHUNK, tile * TM);
         }
         __syncwarp();
+        if (c == 0) B2K_TR(ti, 0);
+        if (c == G::NCH - 1) B2K_TR(ti, 1);
         if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
       }
     }
@@ -508,12 +588,16 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if constexpr (PAIR) mbar_wait_cluster(bar(G::B_DEMPTY + b), bph ^ 1u);
       else mbar_wait_p(bar(G::B_DEMPTY + b), bph ^ 1u, prof, pw[0]);
       tc_fence_after();
+      B2K_TR(ti, 13);
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
         if constexpr (PAIR) mbar_wait_cluster(bar(G::B_AFULL + as), aph);
         else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
         tc_fence_after();
+        if (c == 0) B2K_TR(ti, 14);
+        if (c == G::NCH - 2) B2K_TR(ti, 10);
+        if (c == G::NCH - 1) B2K_TR(ti, 11);
         if (elect_one()) {
           const uint32_t a_hi = tmem_base + as * A_COLS;
           const uint32_t a_lo = a_hi + CHUNK;
@@ -542,6 +626,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           }
         }
         __syncwarp();
+        if (c == G::NCH - 1) B2K_TR(ti, 12);
         if (++as == NA) { as = 0; aph ^= 1u; }
       }
     }
@@ -551,6 +636,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const int r = q * 32 + lane;                       // row within the tile == TMEM lane
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     const uint32_t swz = (uint32_t)(r & 7);
+    const uint64_t kSplitA = pack2(8193.f, 8193.f), kSplitB = pack2(-8192.f, -8192.f);
+    (void)kSplitA; (void)kSplitB;
     int xs = 0, as = 0;
     uint32_t xph = 0, aph = 0;
     // PAIR: this CTA's centre half must have landed before its first a_full signal reaches the leader
@@ -577,6 +664,12 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         asm volatile("bar.sync 6, 128;" ::: "memory");
         tc_fence_after();
+        B2K_T0(t_c0);
+        if (warp == W_CONVERT0) { if (c == 0) B2K_TR(ti, 9); if (c + CG >= G::NCH) B2K_TR(ti, 2); }
+        // need_cost is hoisted out of the element loop (two copies of the body): a per-float4 branch costs as
+        // much issue bandwidth as a fifth of the split itself
+        auto convert_group = [&](auto nc_tag) {
+          constexpr bool NC = decltype(nc_tag)::value;
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
           const uint32_t rowaddr = ring + xs_g[g] * SLOT_BYTES + (uint32_t)r * 128u;
@@ -590,6 +683,27 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
               const int j = h * 4 + j2;
               float4 v = lds128(rowaddr + (((uint32_t)j ^ swz) << 4));
               float e[4] = {v.x, v.y, v.z, v.w};
+#if B2K_PACKED_SPLIT
+              // Veltkamp split with packed fp32 pairs: t = fl(8193 x); hi = t - 8192 x (one FFMA2, exact) is x rounded
+              // to nearest at 11 significant bits = a tf32 value (the tensor core's truncation is then a no-op);
+              // l = x - hi is exact.  lo = RN_tf32(l) through the +1/2 ulp word trick (hardware truncates).
+              // 2.5 issue slots per element instead of 4.
+#pragma unroll
+              for (int t = 0; t < 4; t += 2) {
+                const uint64_t x2 = pack2(e[t], e[t + 1]);
+                const uint64_t t2 = mul2(x2, kSplitA);
+                const uint64_t h2 = fma2(x2, kSplitB, t2);
+                const uint64_t l2 = sub2(x2, h2);
+                float h0, h1, l0, l1;
+                unpack2(h2, h0, h1);
+                unpack2(l2, l0, l1);
+                hi[j2 * 4 + t] = __float_as_uint(h0);
+                hi[j2 * 4 + t + 1] = __float_as_uint(h1);
+                lo[j2 * 4 + t] = __float_as_uint(l0) + 0x1000u;
+                lo[j2 * 4 + t + 1] = __float_as_uint(l1) + 0x1000u;
+                if constexpr (NC) xn = fmaf(e[t + 1], e[t + 1], fmaf(e[t], e[t], xn));
+              }
+#else
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 // The tensor core TRUNCATES fp32 operands to tf32 (measured: tools/probe_trunc.py).  Adding half a
@@ -602,16 +716,23 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 const float l = e[t] - __uint_as_float(hs & 0xffffe000u);   // exact
                 hi[j2 * 4 + t] = hs;
                 lo[j2 * 4 + t] = __float_as_uint(l) + 0x1000u;
-                if (need_cost) xn = fmaf(e[t], e[t], xn);
+                if constexpr (NC) xn = fmaf(e[t], e[t], xn);
               }
+#endif
             }
             tmem_st_x16(a_addr + h * 16, hi);
             tmem_st_x16(a_addr + CHUNK + h * 16, lo);
           }
         }
+        };
+        if (need_cost) convert_group(std::true_type{});
+        else convert_group(std::false_type{});
         tmem_wait_st();
         tc_fence_before();
-        asm volatile("bar.sync 3, 128;" ::: "memory");   // the 4 convert warps (hardware barrier: no polling)
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        B2K_T0(t_c1);
+        if (warp == W_CONVERT0 && c + CG >= G::NCH) B2K_TR(ti, 3);
+        B2K_TACC(3, t_c1 - t_c0);                  // whole group: loads + split + st + wait + barrier   // the 4 convert warps (hardware barrier: no polling)
         if (warp == W_CONVERT0 && lane == 0) {            // one arrival per role keeps the waiters' wake-ups low
 #pragma unroll
           for (int g = 0; g < CG; ++g) {
@@ -620,6 +741,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
             mbar_arrive(bar(G::B_XEMPTY + xs_g[g]));
           }
         }
+        B2K_TACC(4, clock64() - t_c1);              // signalling (leader: remote + local arrives)
       }
       if (need_cost) {
         mbar_wait_p(bar(G::B_NEMPTY + b), bph ^ 1u, prof, pw[2]);
@@ -641,24 +763,37 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if (warp == W_EPI0) mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
       asm volatile("bar.sync 5, 128;" ::: "memory");
       tc_fence_after();
+      B2K_T0(t_e0);
+      if (warp == W_EPI0) B2K_TR(ti, 4);
       float best = __int_as_float(0x7f800000);
       int bj = 0;
+      // argmin over j in index order with strict '<' (lowest index wins ties).  Four independent chains of 8
+      // consecutive candidates, merged in ascending order, give the same winner with a 12-deep instead of a
+      // 32-deep dependent compare/select chain per 32 columns.
 #pragma unroll
       for (int g = 0; g < KP / 32; ++g) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_field + (uint32_t)(D_OFF + b * KP + g * 32), v);
         tmem_wait_ld();
+        float cb[4];
+        int ci[4];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 cn4 = *reinterpret_cast<const float4*>(cnorm_s + g * 32 + j4 * 4);
-          const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+        for (int q4 = 0; q4 < 4; ++q4) {
+          cb[q4] = __int_as_float(0x7f800000);
+          ci[q4] = g * 32 + q4 * 8;
+        }
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int j = j4 * 4 + t;
-            float dist = fmaf(-2.f, __uint_as_float(v[j]), cn[t]);
-            if (dist < best) { best = dist; bj = g * 32 + j; }
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int j = q4 * 8 + jj;
+            const float dist = fmaf(-2.f, __uint_as_float(v[j]), cnorm_s[g * 32 + j]);
+            if (dist < cb[q4]) { cb[q4] = dist; ci[q4] = g * 32 + j; }
           }
         }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          if (cb[q4] < best) { best = cb[q4]; bj = ci[q4]; }
       }
       if constexpr (KP % 32 != 0) {
         // tail group of 16 columns
@@ -672,21 +807,38 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
             : "r"(tmem_base + lane_field + (uint32_t)(D_OFF + b * KP + g * 32))
             : "memory");
         tmem_wait_ld();
+        float cb[2];
+        int ci[2];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float dist = fmaf(-2.f, __uint_as_float(v[j]), cnorm_s[g * 32 + j]);
-          if (dist < best) { best = dist; bj = g * 32 + j; }
+        for (int q4 = 0; q4 < 2; ++q4) {
+          cb[q4] = __int_as_float(0x7f800000);
+          ci[q4] = g * 32 + q4 * 8;
         }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const int j = q4 * 8 + jj;
+            const float dist = fmaf(-2.f, __uint_as_float(v[j]), cnorm_s[g * 32 + j]);
+            if (dist < cb[q4]) { cb[q4] = dist; ci[q4] = g * 32 + j; }
+          }
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4)
+          if (cb[q4] < best) { best = cb[q4]; bj = ci[q4]; }
       }
       tc_fence_before();
+      B2K_T0(t_e1);
+      if (warp == W_EPI0) B2K_TR(ti, 5);
+      B2K_TACC(3, t_e1 - t_e0);                    // TMEM load + argmin
 
       const int64_t grow = (int64_t)tile * TM + r;
       const bool valid = grow < args.n;
       // ---- deterministic counting sort of the tile's rows by (owner update warp, owned-cluster slot, row) ----
       // key = keytab[label] (size-balanced, see k_balance_table): update warp u owns the key range [u*CPW, (u+1)*CPW)
       uint8_t* cnt = sort_s + (ti & 1) * 512;            // [4 warps][128] per-warp key histogram (parity buffered)
-      uint8_t* rows_sorted = sort_s + 1024 + b * 128;    // [128] row ids in key order
-      uint8_t* start = sort_s + 1280 + b * 192;          // [KP + 1] exclusive offsets per key
+      uint16_t* rows_sorted = reinterpret_cast<uint16_t*>(sort_s + SORT_ROWS) + b * 128;   // [128] rows in key order
+      uint8_t* start = sort_s + SORT_START + b * 192;    // [KP + 1] exclusive offsets per key
       if (lane < KP / 4) reinterpret_cast<uint32_t*>(cnt + q * 128)[lane] = 0u;
       __syncwarp();
       const int key = valid ? (int)keytab_s[bj] : KP;
@@ -728,8 +880,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         for (int q2 = 0; q2 < 3; ++q2)
           if (q2 < q) pos += (int)cnt[q2 * 128 + key];
       }
-      if (args.probe != 3) mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
-      if (valid) rows_sorted[pos] = (uint8_t)r;
+      mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
+      if (valid) rows_sorted[pos] = (uint16_t)(r * 128 + ((r & 7) << 4));
       if (q == 0) {
 #pragma unroll
         for (int i = 0; i < G::KPL; ++i) {
@@ -740,6 +892,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       }
       asm volatile("bar.sync 4, 128;" ::: "memory");      // row list complete
       if (warp == W_EPI0 && lane == 0) mbar_arrive(bar(G::B_LFULL + b));
+      if (warp == W_EPI0) B2K_TR(ti, 6);
+      B2K_TACC(4, clock64() - t_e1);               // sort (includes the lab_empty wait counted in pw[2])
       // off the critical path: outputs and cost
       if (valid && args.labels_out) args.labels_out[grow] = bj;
       if (need_cost) {
@@ -761,58 +915,50 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   } else if (warp < W_TMA) {
     // ======================= update warps: per-cluster sums in registers =======================
     const int u = warp - W_UPD0;
-    float4 acc[G::CPW][G::UPL];
+    uint64_t acc[G::CPW][G::UPL][2];   // packed fp32 pairs (x,y) (z,w): one FADD2 adds two columns
     int cnt[G::CPW];
 #pragma unroll
     for (int c = 0; c < G::CPW; ++c) {
       cnt[c] = 0;
 #pragma unroll
-      for (int i = 0; i < G::UPL; ++i) acc[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < G::UPL; ++i) acc[c][i][0] = acc[c][i][1] = 0ull;
+    }
+    // this lane's float4 units of a row: (chunk, 16-B unit inside the 128-B swizzle line) are fixed per lane
+    int unit_cc[G::UPL];
+    uint32_t unit_js[G::UPL];
+#pragma unroll
+    for (int i = 0; i < G::UPL; ++i) {
+      const int unit = lane + 32 * i;
+      unit_cc[i] = unit >> 3;
+      unit_js[i] = (uint32_t)(unit & 7) << 4;
     }
     int xs = 0;
-    uint32_t xph = 0;
     for (int ti = 0; ti < nit; ++ti) {
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       // one warp polls the mbarrier, the other 15 park in a hardware barrier (no issue slots, no wake-ups)
-      if (warp == W_UPD0 && args.probe != 3) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
+      if (warp == W_UPD0) mbar_wait_p(bar(G::B_LFULL + b), bph, prof, pw[0]);
       asm volatile("bar.sync 7, 512;" ::: "memory");
-      // slots of this tile's chunks.  Their x_full phases completed before the convert warps consumed them, which
+      // The x_full phases of this tile's slots completed before the convert warps consumed them, which
       // happens-before the MMA commit, the epilogue and hence this tile's lab_full: no need to poll them again.
-      uint32_t slot_addr[G::NCH];
-      {
-        int s2 = xs;
-        uint32_t p2 = xph;
-#pragma unroll
-        for (int c = 0; c < G::NCH; ++c) {
-          if (args.probe == 3) mbar_wait_p(bar(G::B_XFULL + s2), p2, prof, pw[1]);
-          slot_addr[c] = ring + s2 * SLOT_BYTES;
-          if (++s2 == G::NSLOT) { s2 = 0; p2 ^= 1u; }
-        }
-      }
+      B2K_T0(t_w0);
+      if (warp == W_UPD0) B2K_TR(ti, 7);
       if (args.do_update) {
-        const uint8_t* rows_sorted = sort_s + 1024 + b * 128;
-        const uint8_t* start = sort_s + 1280 + b * 192;
-        // this lane's float4 units of a row: slot base + 16-B unit index inside the 128-B swizzle line
+        const uint16_t* rows_sorted = reinterpret_cast<const uint16_t*>(sort_s + SORT_ROWS) + b * 128;
+        const uint8_t* start = sort_s + SORT_START + b * 192;
         uint32_t unit_base[G::UPL];
-        uint32_t unit_j[G::UPL];
 #pragma unroll
         for (int i = 0; i < G::UPL; ++i) {
-          const int unit = lane + 32 * i;
-          const int cc = unit >> 3;
-          uint32_t sa = slot_addr[0];
-#pragma unroll
-          for (int c2 = 1; c2 < G::NCH; ++c2) sa = (cc == c2) ? slot_addr[c2] : sa;
-          unit_base[i] = sa;
-          unit_j[i] = (uint32_t)(unit & 7);
+          int s2 = xs + unit_cc[i];
+          if (s2 >= G::NSLOT) s2 -= G::NSLOT;
+          unit_base[i] = ring + (uint32_t)s2 * SLOT_BYTES;
         }
-        auto load_row = [&](int row, float4 (&v)[G::UPL]) {
+        // roff = row * 128 + ((row & 7) << 4) (written by the epilogue): address = slot + (roff ^ (unit << 4))
+        auto load_row = [&](uint32_t roff, uint64_t (&v)[G::UPL][2]) {
 #pragma unroll
           for (int i = 0; i < G::UPL; ++i) {
-            if (lane + 32 * i < DP / 4)
-              v[i] = lds128(unit_base[i] + (uint32_t)row * 128u + ((unit_j[i] ^ (uint32_t)(row & 7)) << 4));
-            else
-              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane + 32 * i < DP / 4) lds128_2(unit_base[i] + (roff ^ unit_js[i]), v[i][0], v[i][1]);
+            else v[i][0] = v[i][1] = 0ull;
           }
         };
         // segment bounds of my CPW owned clusters: start[u*CPW .. u*CPW + CPW]
@@ -824,25 +970,31 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           cnt[c] += i1 - i0;
           for (int i = i0; i < i1; i += 2) {      // rows of one cluster, ascending row order, two in flight
             const bool two = (i + 1 < i1);
-            const int r0 = (int)rows_sorted[i];
-            const int r1 = (int)rows_sorted[two ? i + 1 : i];
-            float4 v0[G::UPL], v1[G::UPL];
+            const uint32_t r0 = rows_sorted[i];
+            const uint32_t r1 = rows_sorted[two ? i + 1 : i];
+            uint64_t v0[G::UPL][2], v1[G::UPL][2];
             load_row(r0, v0);
             load_row(r1, v1);
 #pragma unroll
             for (int k2 = 0; k2 < G::UPL; ++k2) {
-              acc[c][k2].x += v0[k2].x; acc[c][k2].y += v0[k2].y; acc[c][k2].z += v0[k2].z; acc[c][k2].w += v0[k2].w;
+              acc[c][k2][0] = add2(acc[c][k2][0], v0[k2][0]);
+              acc[c][k2][1] = add2(acc[c][k2][1], v0[k2][1]);
             }
             if (two) {
 #pragma unroll
               for (int k2 = 0; k2 < G::UPL; ++k2) {
-                acc[c][k2].x += v1[k2].x; acc[c][k2].y += v1[k2].y; acc[c][k2].z += v1[k2].z; acc[c][k2].w += v1[k2].w;
+                acc[c][k2][0] = add2(acc[c][k2][0], v1[k2][0]);
+                acc[c][k2][1] = add2(acc[c][k2][1], v1[k2][1]);
               }
             }
           }
         }
       }
+      B2K_T0(t_w1);
+      B2K_TACC(3, t_w1 - t_w0);                    // this warp's rows
       asm volatile("bar.sync 2, 512;" ::: "memory");     // the 16 update warps
+      B2K_TACC(4, clock64() - t_w1);               // waiting for the slowest warp
+      if (warp == W_UPD0) B2K_TR(ti, 8);
       if (warp == W_UPD0 && lane == 0) {
         mbar_arrive(bar(G::B_LEMPTY + b));
         int s2 = xs;
@@ -852,9 +1004,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           if (++s2 == G::NSLOT) s2 = 0;
         }
       }
-#pragma unroll
-      for (int c = 0; c < G::NCH; ++c)
-        if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
+      xs += G::NCH;
+      if (xs >= G::NSLOT) xs -= G::NSLOT;
     }
     // flush: partials[cta][l][col..col+3], l = u + 8*c
     if (args.do_update) {
@@ -866,7 +1017,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #pragma unroll
           for (int i = 0; i < G::UPL; ++i) {
             const int col = (lane + 32 * i) * 4;
-            float e[4] = {acc[c][i].x, acc[c][i].y, acc[c][i].z, acc[c][i].w};
+            float e[4];
+            unpack2(acc[c][i][0], e[0], e[1]);
+            unpack2(acc[c][i][1], e[2], e[3]);
 #pragma unroll
             for (int t = 0; t < 4; ++t)
               if (col + t < args.d) out[(size_t)l * args.d + col + t] = e[t];
@@ -1088,9 +1241,9 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.prof = nullptr;
   if (ctx->profile_fused) {
     if (!ctx->prof_dev) B2K_CUDA_OK(ctx, cudaMalloc(&ctx->prof_dev, (size_t)1024 * NWARPS * 8 * sizeof(long long)));
-    B2K_CUDA_OK(ctx, cudaMemsetAsync(ctx->prof_dev, 0, (size_t)plan.grid * NWARPS * 8 * sizeof(long long), s));
+    B2K_CUDA_OK(ctx, cudaMemsetAsync(ctx->prof_dev, 0, (size_t)(plan.grid + B2K_TRACE_CTAS) * NWARPS * 8 * sizeof(long long), s));
     a.prof = ctx->prof_dev;
-    ctx->prof_grid = plan.grid;
+    ctx->prof_grid = plan.grid + B2K_TRACE_CTAS;   // (+ trace area in diagnostic builds)
   }
 
   int rc = B2K_ERR_UNSUPPORTED;
