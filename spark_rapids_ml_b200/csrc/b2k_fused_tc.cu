@@ -32,6 +32,13 @@ namespace {
 // Diagnostic build (make trace -> libb2kmeans_trace.so): per-stage cycle counters and a per-tile event trace on top of
 // the blocked-cycle counters of option "profile_fused".  Off in the product build: even the predicated-off timer
 // reads cost ~10 % of the kernel's speed (register pressure in the convert / epilogue loops; measured).
+// -DB2K_PROBE=1: timing experiments selected by option "probe" (they skip work: WRONG results; never in the product)
+#ifndef B2K_PROBE
+#define B2K_PROBE 0
+#endif
+#ifndef B2K_MMA_WAIT
+#define B2K_MMA_WAIT mbar_wait_cluster   // alternative: mbar_spin (CTA-scope test_wait loop; same speed, measured)
+#endif
 #ifndef B2K_TRACE
 #define B2K_TRACE 0
 #endif
@@ -323,6 +330,24 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t
       : "memory");
   return ok;
 }
+// Dedicated single-warp poller (the MMA issuer): non-blocking test in a tight loop, CTA-scope acquire.  What these
+// waits order is TMEM traffic (tcgen05 fences on both sides), and the phase flips in this CTA's own shared memory
+// whoever arrives.  Kept as an alternative to mbar_wait_cluster (B2K_MMA_WAIT): same step time, measured.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins == (1u << 24)) mbar_timeout(bar, parity);
+  }
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
@@ -585,14 +610,14 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     for (int ti = 0; ti < ((PAIR && rank != 0) ? 0 : nit); ++ti) {   // PAIR: only the leader CTA issues
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
-      if constexpr (PAIR) mbar_wait_cluster(bar(G::B_DEMPTY + b), bph ^ 1u);
+      if constexpr (PAIR) B2K_MMA_WAIT(bar(G::B_DEMPTY + b), bph ^ 1u);
       else mbar_wait_p(bar(G::B_DEMPTY + b), bph ^ 1u, prof, pw[0]);
       tc_fence_after();
       B2K_TR(ti, 13);
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-        if constexpr (PAIR) mbar_wait_cluster(bar(G::B_AFULL + as), aph);
+        if constexpr (PAIR) B2K_MMA_WAIT(bar(G::B_AFULL + as), aph);
         else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
         tc_fence_after();
         if (c == 0) B2K_TR(ti, 14);
@@ -608,6 +633,14 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const uint64_t dhi = make_kmajor_sw128_desc(bhi + ks * 32);
             const uint64_t dlo = make_kmajor_sw128_desc(blo + ks * 32);
             if constexpr (PAIR) {
+#if B2K_PROBE   // probe 4 / 5: only 1 / 2 of the 3 products
+              if (args.probe == 4) { tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u); continue; }
+              if (args.probe == 5) {
+                tc_mma_ts_tf32_pair(d_tmem, a_lo + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u);
+                tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dhi, idesc, 1u);
+                continue;
+              }
+#endif
               tc_mma_ts_tf32_pair(d_tmem, a_lo + ks * 8, dhi, idesc, (c | ks) != 0 ? 1u : 0u);
               tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dlo, idesc, 1u);
               tc_mma_ts_tf32_pair(d_tmem, a_hi + ks * 8, dhi, idesc, 1u);
@@ -725,6 +758,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           }
         }
         };
+#if B2K_PROBE
+        if (args.probe == 9) { /* skip */ } else
+#endif
         if (need_cost) convert_group(std::true_type{});
         else convert_group(std::false_type{});
         tmem_wait_st();
@@ -767,6 +803,10 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if (warp == W_EPI0) B2K_TR(ti, 4);
       float best = __int_as_float(0x7f800000);
       int bj = 0;
+#if B2K_PROBE
+      if (args.probe == 8) { bj = r & (KP - 1); best = 0.f; } else
+#endif
+      {
       // argmin over j in index order with strict '<' (lowest index wins ties).  Four independent chains of 8
       // consecutive candidates, merged in ascending order, give the same winner with a 12-deep instead of a
       // 32-deep dependent compare/select chain per 32 columns.
@@ -826,6 +866,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4)
           if (cb[q4] < best) { best = cb[q4]; bj = ci[q4]; }
+      }
       }
       tc_fence_before();
       B2K_T0(t_e1);
@@ -943,7 +984,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       // happens-before the MMA commit, the epilogue and hence this tile's lab_full: no need to poll them again.
       B2K_T0(t_w0);
       if (warp == W_UPD0) B2K_TR(ti, 7);
-      if (args.do_update) {
+      if (args.do_update && !(B2K_PROBE && args.probe == 6)) {
         const uint16_t* rows_sorted = reinterpret_cast<const uint16_t*>(sort_s + SORT_ROWS) + b * 128;
         const uint8_t* start = sort_s + SORT_START + b * 192;
         uint32_t unit_base[G::UPL];
