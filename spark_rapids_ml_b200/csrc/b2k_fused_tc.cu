@@ -703,10 +703,11 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         // much issue bandwidth as a fifth of the split itself
         auto convert_group = [&](auto nc_tag) {
           constexpr bool NC = decltype(nc_tag)::value;
-#pragma unroll
+#pragma unroll 1   // code size (instruction fetch)
         for (int g = 0; g < CG; ++g) {
-          const uint32_t rowaddr = ring + xs_g[g] * SLOT_BYTES + (uint32_t)r * 128u;
-          const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(as_g[g] * A_COLS);
+          const int xsg = (g == 0) ? xs_g[0] : xs_g[CG - 1], asg = (g == 0) ? as_g[0] : as_g[CG - 1];
+          const uint32_t rowaddr = ring + xsg * SLOT_BYTES + (uint32_t)r * 128u;
+          const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(asg * A_COLS);
           // halves of 16 columns: bounds the live registers (the CTA runs 26 warps at 72 registers/thread)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -810,7 +811,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       // argmin over j in index order with strict '<' (lowest index wins ties).  Four independent chains of 8
       // consecutive candidates, merged in ascending order, give the same winner with a 12-deep instead of a
       // 32-deep dependent compare/select chain per 32 columns.
-#pragma unroll
+#pragma unroll 1   // code size: the kernel is instruction-fetch sensitive (stall_no_inst), see DESIGN.md
       for (int g = 0; g < KP / 32; ++g) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_field + (uint32_t)(D_OFF + b * KP + g * 32), v);
