@@ -465,7 +465,9 @@ struct FusedArgs {
   long long* prof;         // [grid][NWARPS][8] cycle counters or NULL
 };
 
-template <int KP, int DP, bool PAIR>
+// NC: the pass also produces ||x||^2, the min distance and the cost partial (assign / inertia passes); a template
+// parameter rather than a run-time flag so that the Lloyd-loop kernel carries none of that code (code size).
+template <int KP, int DP, bool PAIR, bool NC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapChi,
                       const __grid_constant__ CUtensorMap mapClo, const FusedArgs args) {
@@ -488,8 +490,12 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#if B2K_TRACE
   const bool prof = args.prof != nullptr;
-  const bool need_cost = args.need_cost != 0;
+#else
+  constexpr bool prof = false;   // the cycle counters exist in the diagnostic build only (they cost speed: code size)
+#endif
+  constexpr bool need_cost = NC;
   long long pw[6] = {0, 0, 0, 0, 0, 0};   // blocked cycles per barrier kind (role specific)
   const long long t_role0 = prof ? clock64() : 0;
 #if B2K_TRACE
@@ -571,23 +577,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __syncwarp();
     int xs = 0;
     uint32_t xph = 0;
-    const int PF = args.pf_dist;   // tiles of L2 look-ahead beyond what the ring already holds (< 0: no prefetch)
-    if (PF >= 0 && elect_one()) {
-      for (int p = 0; p < PF + 2; ++p) {
-        const int pt = tile_of(p);
-        if (p < nit && pt < args.ntiles)
-          for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
-      }
-    }
-    __syncwarp();
     for (int ti = 0; ti < nit; ++ti) {
       const int tile = tile_of(ti);
-      if (PF >= 0 && elect_one()) {
-        const int pt = tile_of(ti + PF + 2);
-        if (ti + PF + 2 < nit && pt < args.ntiles)
-          for (int c = 0; c < G::NCH; ++c) tma_prefetch_l2_2d(&mapX, c * CHUNK, pt * TM);
-      }
-      __syncwarp();
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
         mbar_wait_p(bar(G::B_XEMPTY + xs), xph ^ 1u, prof, pw[0]);
@@ -762,8 +753,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #if B2K_PROBE
         if (args.probe == 9) { /* skip */ } else
 #endif
-        if (need_cost) convert_group(std::true_type{});
-        else convert_group(std::false_type{});
+        convert_group(std::integral_constant<bool, NC>{});
         tmem_wait_st();
         tc_fence_before();
         asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -1151,11 +1141,11 @@ bool pick_inst(int d, int k, Inst* out) {
   return true;
 }
 
-template <int KP, int DP, bool PAIR>
-int launch_inst(b2k_ctx* ctx, int grid, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml,
+template <int KP, int DP, bool PAIR, bool NC>
+int launch_inst_nc(b2k_ctx* ctx, int grid, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml,
                 const FusedArgs& a, cudaStream_t s) {
   using G = Cfg<KP, DP, PAIR>;
-  auto kern = k_fused_assign_update<KP, DP, PAIR>;
+  auto kern = k_fused_assign_update<KP, DP, PAIR, NC>;
   B2K_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
   if constexpr (PAIR) {
     cudaLaunchConfig_t cfg{};
@@ -1176,6 +1166,13 @@ int launch_inst(b2k_ctx* ctx, int grid, const CUtensorMap& mx, const CUtensorMap
   }
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
+}
+
+template <int KP, int DP, bool PAIR>
+int launch_inst(b2k_ctx* ctx, int grid, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml,
+                const FusedArgs& a, cudaStream_t s) {
+  return a.need_cost ? launch_inst_nc<KP, DP, PAIR, true>(ctx, grid, mx, mh, ml, a, s)
+                     : launch_inst_nc<KP, DP, PAIR, false>(ctx, grid, mx, mh, ml, a, s);
 }
 
 struct PlanLayout {
@@ -1281,6 +1278,8 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.need_cost = (!do_update || mindist_out != nullptr) ? 1 : 0;
   a.st = st;
   a.prof = nullptr;
+  if (ctx->profile_fused && !B2K_TRACE)
+    return b2k_fail(ctx, B2K_ERR_UNSUPPORTED, "profile_fused needs the diagnostic build (make trace; B2K_LIB=libb2kmeans_trace.so)");
   if (ctx->profile_fused) {
     if (!ctx->prof_dev) B2K_CUDA_OK(ctx, cudaMalloc(&ctx->prof_dev, (size_t)1024 * NWARPS * 8 * sizeof(long long)));
     B2K_CUDA_OK(ctx, cudaMemsetAsync(ctx->prof_dev, 0, (size_t)(plan.grid + B2K_TRACE_CTAS) * NWARPS * 8 * sizeof(long long), s));
