@@ -1000,6 +1000,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
           const int i0 = __shfl_sync(0xffffffffu, sv, c);
           const int i1 = __shfl_sync(0xffffffffu, sv, c + 1);
           cnt[c] += i1 - i0;
+#pragma unroll 1   // typical trip count 1-2; ptxas would otherwise unroll it 4x (code size)
           for (int i = i0; i < i1; i += 2) {      // rows of one cluster, ascending row order, two in flight
             const bool two = (i + 1 < i1);
             const uint32_t r0 = rows_sorted[i];
