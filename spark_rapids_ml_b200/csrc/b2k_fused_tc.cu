@@ -57,7 +57,7 @@ namespace {
 #define B2K_PACKED_SPLIT 1
 #endif
 #ifndef B2K_NSLOT_CAP
-#define B2K_NSLOT_CAP 12
+#define B2K_NSLOT_CAP 13
 #endif
 constexpr int TM = 128;            // rows per tile (UMMA M)
 constexpr int CHUNK = 32;          // f32 per 128-byte swizzle row = one TMA box / K chunk
@@ -77,14 +77,23 @@ constexpr int NWARPS = 26;              // 832 threads -> 72 registers per threa
 constexpr int NTHREADS = NWARPS * 32;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-// counting-sort scratch (epilogue -> update hand-off), byte offsets inside it:
-//   [0, 1024)      per-warp key histograms, parity buffered: u8 [2][4][128]
-//   [1024, 1536)   sorted row list, double buffered: u16 [2][128]; an entry is the row's byte offset inside a ring
-//                  slot with its swizzle phase folded in: row * 128 + ((row & 7) << 4)
-//   [1536, 1920)   exclusive start offset per sort key, double buffered: u8 [2][192]
-//   [1920, 2048)   keytab u8 [128]      [2048, 2176)   keyinv u8 [128]
-constexpr int SORT_BYTES = 2304;
-constexpr int SORT_ROWS = 1024, SORT_START = 1536, SORT_KEYTAB = 1920, SORT_KEYINV = 2048;
+// Counting-sort scratch (epilogue -> update hand-off), sized by KP so that the (64, 128, PAIR) instantiation fits a
+// 12th ring slot (every byte counts there: see Cfg):
+//   CNT     per-warp key histograms, parity buffered: u8 [2][4][KP]
+//   ROWS    sorted row list, double buffered: u16 [2][128]; an entry is the row's byte offset inside a ring slot with
+//           its swizzle phase folded in: row * 128 + ((row & 7) << 4)
+//   START   exclusive start offset per sort key, double buffered: u8 [2][SP], SP = KP + 1 rounded up to 16
+//   KEYTAB  u8 [KP]      KEYINV  u8 [KP]
+template <int KP>
+struct SortLayout {
+  static constexpr int SP = (KP + 16) & ~15;
+  static constexpr int CNT = 0;
+  static constexpr int ROWS = 8 * KP;
+  static constexpr int START = ROWS + 512;
+  static constexpr int KEYTAB = START + 2 * SP;
+  static constexpr int KEYINV = KEYTAB + KP;
+  static constexpr int BYTES = KEYINV + KP;
+};
 
 template <int KP, int DP, bool PAIR = false>
 struct Cfg {
@@ -96,16 +105,19 @@ struct Cfg {
   static_assert(DP % CHUNK == 0 && DP >= CHUNK && DP <= 256, "DP");
   static constexpr int NCH = DP / CHUNK;
   static constexpr int C_BYTES = KPS * DP * 4;                 // one of Chi / Clo (this CTA's share)
-  static constexpr int MISC = 1024 /*labels*/ + 1024 /*xnorm*/ + KP * 4 + 512 /*barriers*/ + 64 + SORT_BYTES;
-  static constexpr int NSLOT_RAW = (int)((SMEM_LIMIT - 1024 - 2 * C_BYTES - MISC) / SLOT_BYTES);
+  using SL = SortLayout<KP>;
+  static constexpr int BAR_BYTES = 384;                        // up to 48 mbarriers
+  // The dynamic shared memory base is required to be 1 KB aligned (checked at kernel entry; it is: the kernel has no
+  // static shared memory), so there is no alignment slack.
+  static constexpr int MISC = 1024 /*xnorm*/ + KP * 4 + BAR_BYTES + 64 + SL::BYTES;
+  static constexpr int NSLOT_RAW = (int)((SMEM_LIMIT - 2 * C_BYTES - MISC) / SLOT_BYTES);
   static constexpr int NSLOT = NSLOT_RAW > B2K_NSLOT_CAP ? B2K_NSLOT_CAP : NSLOT_RAW;
   static_assert(NSLOT >= NCH + 1, "ring too small");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_CHI = NSLOT * SLOT_BYTES;
   static constexpr int OFF_CLO = OFF_CHI + C_BYTES;
   static constexpr int OFF_CNORM = OFF_CLO + C_BYTES;
-  static constexpr int OFF_LABELS = OFF_CNORM + KP * 4;
-  static constexpr int OFF_XNORM = OFF_LABELS + 1024;
+  static constexpr int OFF_XNORM = OFF_CNORM + KP * 4;
   static constexpr int OFF_BARS = OFF_XNORM + 1024;
   // barrier indices (8 bytes each)
   static constexpr int B_XFULL = 0;
@@ -120,16 +132,18 @@ struct Cfg {
   static constexpr int B_NEMPTY = B_NFULL + 2;
   static constexpr int B_CFULL = B_NEMPTY + 2;
   static constexpr int NBARS = B_CFULL + 1;
-  static_assert(NBARS * 8 <= 512, "barrier area");
-  static constexpr int OFF_TMEMPTR = OFF_BARS + 512;
+  static_assert(NBARS * 8 <= BAR_BYTES, "barrier area");
+  static constexpr int OFF_TMEMPTR = OFF_BARS + BAR_BYTES;
   static constexpr int OFF_SORT = OFF_TMEMPTR + 64;            // counting-sort scratch (epilogue -> update)
-  static constexpr int SMEM_BYTES = OFF_SORT + SORT_BYTES + 1024;   // +1024: manual 1 KB alignment slack
+  static constexpr int SMEM_BYTES = OFF_SORT + SL::BYTES;
   static_assert(SMEM_BYTES <= (int)SMEM_LIMIT, "smem");
   static constexpr int UPL = (DP / 4 + 31) / 32;   // float4 units per lane in the update warps
   static constexpr int CPW = (KP + N_UPD - 1) / N_UPD;  // clusters per update warp
   static constexpr int KPL = (KP + 31) / 32;            // sort keys per lane in the epilogue scan
   static_assert(KP % N_UPD == 0, "KP must be a multiple of the update warp count");
 };
+
+static_assert(Cfg<64, 128, true>::NSLOT == 12, "the flagship instantiation is laid out for a 12-slot (3-tile) ring");
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -474,14 +488,17 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
   using G = Cfg<KP, DP, PAIR>;
   if (args.st != nullptr && args.st->done) return;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* gbase = smem_raw;
+  if ((base & 1023u) != 0u) {   // 128B-swizzle atoms (TMA boxes, UMMA descriptors) need 1 KB alignment
+    if (threadIdx.x == 0) printf("b2k fused: dynamic shared memory base %u is not 1 KB aligned\n", base);
+    __trap();
+  }
   const uint32_t ring = base + G::OFF_RING;
   const uint32_t chi_s = base + G::OFF_CHI;
   const uint32_t clo_s = base + G::OFF_CLO;
   float* cnorm_s = reinterpret_cast<float*>(gbase + G::OFF_CNORM);
-  int* labels_s = reinterpret_cast<int*>(gbase + G::OFF_LABELS);     // [2][128]
   float* xnorm_s = reinterpret_cast<float*>(gbase + G::OFF_XNORM);   // [2][128]
   const uint32_t bars = base + G::OFF_BARS;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(gbase + G::OFF_TMEMPTR);
@@ -544,8 +561,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
     }
   }
   for (int j = threadIdx.x; j < KP; j += NTHREADS) cnorm_s[j] = args.cnorm[j];
-  uint8_t* keytab_s = sort_s + SORT_KEYTAB;   // [KP]
-  uint8_t* keyinv_s = sort_s + SORT_KEYINV;   // [KP]
+  using SL = typename G::SL;
+  uint8_t* keytab_s = sort_s + SL::KEYTAB;   // [KP]
+  uint8_t* keyinv_s = sort_s + SL::KEYINV;   // [KP]
   for (int j = threadIdx.x; j < KP; j += NTHREADS) { keytab_s[j] = args.keytab[j]; keyinv_s[j] = args.keyinv[j]; }
   tc_fence_before();
   __syncthreads();
@@ -868,15 +886,15 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const bool valid = grow < args.n;
       // ---- deterministic counting sort of the tile's rows by (owner update warp, owned-cluster slot, row) ----
       // key = keytab[label] (size-balanced, see k_balance_table): update warp u owns the key range [u*CPW, (u+1)*CPW)
-      uint8_t* cnt = sort_s + (ti & 1) * 512;            // [4 warps][128] per-warp key histogram (parity buffered)
-      uint16_t* rows_sorted = reinterpret_cast<uint16_t*>(sort_s + SORT_ROWS) + b * 128;   // [128] rows in key order
-      uint8_t* start = sort_s + SORT_START + b * 192;    // [KP + 1] exclusive offsets per key
-      if (lane < KP / 4) reinterpret_cast<uint32_t*>(cnt + q * 128)[lane] = 0u;
+      uint8_t* cnt = sort_s + SL::CNT + (ti & 1) * (4 * KP);   // [4 warps][KP] per-warp key histogram (parity buffered)
+      uint16_t* rows_sorted = reinterpret_cast<uint16_t*>(sort_s + SL::ROWS) + b * 128;   // [128] rows in key order
+      uint8_t* start = sort_s + SL::START + b * SL::SP;    // [KP + 1] exclusive offsets per key
+      if (lane < KP / 4) reinterpret_cast<uint32_t*>(cnt + q * KP)[lane] = 0u;
       __syncwarp();
       const int key = valid ? (int)keytab_s[bj] : KP;
       const uint32_t same = __match_any_sync(0xffffffffu, key);
       const int rank = __popc(same & ((1u << lane) - 1u));
-      if (valid && rank == 0) cnt[q * 128 + key] = (uint8_t)__popc(same);
+      if (valid && rank == 0) cnt[q * KP + key] = (uint8_t)__popc(same);
       asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
       if (warp == W_EPI0 && lane == 0) {   // all four have drained D: it may be overwritten by tile ti+2
         if constexpr (PAIR) mbar_arrive_cluster(bar(G::B_DEMPTY + b), 0u);
@@ -887,7 +905,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #pragma unroll
       for (int i = 0; i < G::KPL; ++i) {
         const int kk = lane * G::KPL + i;
-        tot[i] = (kk < KP) ? (int)cnt[kk] + (int)cnt[128 + kk] + (int)cnt[256 + kk] + (int)cnt[384 + kk] : 0;
+        tot[i] = (kk < KP) ? (int)cnt[kk] + (int)cnt[KP + kk] + (int)cnt[2 * KP + kk] + (int)cnt[3 * KP + kk] : 0;
         lane_sum += tot[i];
       }
       int incl = lane_sum;
@@ -910,7 +928,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if (valid) {
 #pragma unroll
         for (int q2 = 0; q2 < 3; ++q2)
-          if (q2 < q) pos += (int)cnt[q2 * 128 + key];
+          if (q2 < q) pos += (int)cnt[q2 * KP + key];
       }
       mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
       if (valid) rows_sorted[pos] = (uint16_t)(r * 128 + ((r & 7) << 4));
@@ -976,8 +994,8 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       B2K_T0(t_w0);
       if (warp == W_UPD0) B2K_TR(ti, 7);
       if (args.do_update && !(B2K_PROBE && args.probe == 6)) {
-        const uint16_t* rows_sorted = reinterpret_cast<const uint16_t*>(sort_s + SORT_ROWS) + b * 128;
-        const uint8_t* start = sort_s + SORT_START + b * 192;
+        const uint16_t* rows_sorted = reinterpret_cast<const uint16_t*>(sort_s + SL::ROWS) + b * 128;
+        const uint8_t* start = sort_s + SL::START + b * SL::SP;
         uint32_t unit_base[G::UPL];
 #pragma unroll
         for (int i = 0; i < G::UPL; ++i) {
