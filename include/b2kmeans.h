@@ -104,12 +104,15 @@ const char* b2k_last_error(const b2k_ctx* ctx);
 int b2k_ctx_create(int device, b2k_ctx** out);
 int b2k_ctx_destroy(b2k_ctx* ctx);
 /* Options: "kernel_path" (b2k_kernel_path), "time_kernels" (0/1), "check_every" (iterations between host
- * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "profile_fused" (0/1),
- * "pair" (1 = use the CTA-pair tcgen05 cta_group::2 kernel where instantiated, default 1). */
+ * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "pair" (1 = use the
+ * CTA-pair tcgen05 cta_group::2 kernel where instantiated, default 1); diagnostic builds only (`make trace` ->
+ * libb2kmeans_trace.so, `-DB2K_PROBE=1`): "profile_fused" (0/1; the product build rejects it with
+ * B2K_ERR_UNSUPPORTED at the next fused launch), "probe" (timing experiments that skip work). */
 int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value);
 int b2k_get_stats(const b2k_ctx* ctx, b2k_stats* out);
-/* Diagnostics (option "profile_fused"=1): per-CTA, per-warp-role cycle counters of the last fused launch,
- * layout [grid][warps][8] = {role cycles, blocked cycles on up to 6 barrier kinds, 0}. Synchronises the device. */
+/* Diagnostics (diagnostic build + option "profile_fused"=1): per-CTA, per-warp-role cycle counters of the last fused
+ * launch, layout [grid (+4 trace pseudo-CTAs)][warps][8] = {role cycles, 3 blocked-cycle counters, 2 stage timers, 0, 0}.
+ * Synchronises the device. */
 int b2k_get_fused_profile(b2k_ctx* ctx, long long* out, int64_t cap, int* grid_out, int* warps_out);
 int b2k_reset_stats(b2k_ctx* ctx);
 /* Diagnostics: one pass of X[n, d] (d % 32 == 0) through an nslot x 16 KB TMA ring whose slots are released
