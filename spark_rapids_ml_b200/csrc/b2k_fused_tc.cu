@@ -1,15 +1,20 @@
 // Fused assign + per-cluster partial-sum kernel for sm_100a: ONE pass over X per Lloyd iteration.
 //
-//   TMA (cp.async.bulk.tensor, 128B swizzle)  : X row tiles [128 x 32 f32] HBM -> smem ring
-//   convert warps (4)                          : smem -> split x = hi + lo (both RN to tf32) -> TMEM (tcgen05.st)
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  : X row tiles [128 x 32 f32] HBM -> smem ring (12 slots = 3 tiles)
+//   convert warps (4)                          : smem -> split x = hi + lo (both RN to tf32, packed fp32x2 ops)
+//                                                 -> TMEM (tcgen05.st)
 //   MMA warp (1 thread issues)                 : D[128 x KP] (TMEM, fp32) = hi.Chi^T + lo.Chi^T + hi.Clo^T
 //                                                 tcgen05.mma kind::tf32, A from TMEM, B (centers) from smem
 //                                                 => "3xTF32": fp32-accurate x.c without an fp32 tensor mode
 //   epilogue warps (4)                         : tcgen05.ld D -> dist_j = ||c_j||^2 - 2 x.c_j -> argmin
 //                                                 (lowest index on ties) -> labels, min distance, cost
-//   update warps (8)                           : re-read the SAME smem tile, accumulate per-cluster sums in
-//                                                 REGISTERS (warp u owns clusters j%8==u; lane owns 4 columns):
-//                                                 no atomics, deterministic; flushed once per CTA
+//                                                 + deterministic counting sort of the tile's rows by cluster
+//   update warps (16)                          : re-read the SAME smem tile in sorted order, accumulate per-cluster
+//                                                 sums in REGISTERS (warp u owns KP/16 clusters dealt by size; lane
+//                                                 owns 4 columns): no atomics, deterministic; flushed once per CTA
+//
+// The step is a latency ring (TMA -> convert -> MMA -> argmin/sort -> update -> slot release) and is sensitive to
+// instruction fetch: keep the hot loops rolled and diagnostics out of the product build.
 //
 // Persistent: one CTA per SM, static round-robin over row tiles (deterministic partial sums).
 // What it replaces: cuML's fusedL2NN (minClusterAndDistanceCompute) + reduce_rows_by_key second pass over X,
@@ -426,9 +431,9 @@ __global__ void __launch_bounds__(256) k_prep_centers_tc(const float* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // cluster -> (update warp, accumulator slot) table.  The update stage is gated by its most loaded warp, so the
-// clusters are dealt to the 8 update warps by size (descending, snake order: a deterministic LPT-style packing
-// with exactly KP/8 slots per warp).  Sizes = the previous iteration's cluster counts (any positive scaling);
-// without them (first pass) the mapping is the identity j -> (j % 8, j / 8).
+// clusters are dealt to the N_UPD update warps by size (descending, snake order: a deterministic LPT-style packing
+// with exactly KP/N_UPD slots per warp).  Sizes = the previous iteration's cluster counts (any positive scaling);
+// without them (first pass) the mapping is the identity j -> (j % N_UPD, j / N_UPD).
 //   keytab[j]  = owner_warp * CPW + slot        inv[key] = j
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_balance_table(const double* __restrict__ counts, int k, int KP,
@@ -472,8 +477,8 @@ struct FusedArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int do_update;
-  int pf_dist;             // L2 prefetch look-ahead in tiles (-1 = off)
-  int probe;               // EXPERIMENT 3: update warps ignore lab_full/lab_empty (stale row lists; WRONG sums)
+  int pf_dist;             // unused (the L2 prefetch experiment was removed: +35 % DRAM traffic)
+  int probe;               // -DB2K_PROBE=1 builds: timing experiment selector (skips work; wrong results)
   int need_cost;           // compute ||x||^2, min distance and the cost partial (assign / inertia passes)
   const B2kLoopState* st;
   long long* prof;         // [grid][NWARPS][8] cycle counters or NULL
@@ -1058,7 +1063,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       xs += G::NCH;
       if (xs >= G::NSLOT) xs -= G::NSLOT;
     }
-    // flush: partials[cta][l][col..col+3], l = u + 8*c
+    // flush: partials[cta][l][col..col+3] for the owned clusters l = keyinv[u*CPW + c]
     if (args.do_update) {
       float* out = args.partials + (size_t)blockIdx.x * args.k * args.d;
 #pragma unroll

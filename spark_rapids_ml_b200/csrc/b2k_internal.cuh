@@ -39,7 +39,7 @@ struct b2k_ctx {
   int grid_limit = 0;
   int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
   int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
-  int pf_dist = -1;              // option "pf_dist": L2 prefetch look-ahead of the fused kernel in tiles (-1 off)
+  int pf_dist = -1;              // option "pf_dist": accepted, ignored (the L2 prefetch experiment was removed)
   int profile_fused = 0;         // record per-role blocked-cycle counters of the fused kernel
   long long* prof_dev = nullptr;  // [grid][18 warps][8]
   int prof_grid = 0;
