@@ -698,16 +698,26 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #pragma unroll 1
       for (int c = 0; c < G::NCH; c += CG) {
         int xs_g[CG], as_g[CG];
+        uint32_t xp_g[CG], ap_g[CG];
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
           xs_g[g] = xs;
           as_g[g] = as;
-          if (warp == W_CONVERT0) {
-            mbar_wait_p(bar(G::B_XFULL + xs), xph, prof, pw[0]);
-            mbar_wait_p(bar(G::B_AEMPTY + as), aph ^ 1u, prof, pw[1]);
-          }
+          xp_g[g] = xph;
+          ap_g[g] = aph ^ 1u;
           if (++xs == G::NSLOT) { xs = 0; xph ^= 1u; }
           if (++as == NA) { as = 0; aph ^= 1u; }
+        }
+        // The group needs 2*CG barriers (x_full and a_empty per chunk).  Even a completed mbarrier wait costs a few
+        // hundred cycles, and one warp polling them in turn put ~1.4 k cycles per tile on the convert role (measured with
+        // the event trace): each of the four convert warps polls ONE of them, the hardware barrier joins the results.
+        {
+          const int p = warp - W_CONVERT0;
+          if (p < 2 * CG) {
+            const int g = p >> 1;
+            if ((p & 1) == 0) mbar_wait_p(bar(G::B_XFULL + (g == 0 ? xs_g[0] : xs_g[CG - 1])), g == 0 ? xp_g[0] : xp_g[CG - 1], prof, pw[0]);
+            else mbar_wait_p(bar(G::B_AEMPTY + (g == 0 ? as_g[0] : as_g[CG - 1])), g == 0 ? ap_g[0] : ap_g[CG - 1], prof, pw[1]);
+          }
         }
         asm volatile("bar.sync 6, 128;" ::: "memory");
         tc_fence_after();
