@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     return ap.parse_args()
 
 
@@ -329,10 +329,10 @@ def main():
     # ---- CPU baseline (oracle port) on rank 0 at N=1, bounded sample ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = 400_000
-        val, dt, threads = cpu_reference_run(rows, d, k, 5)
+        rows, cpu_iters = args.cpu_sample_rows, 20
+        val, dt, threads = cpu_reference_run(rows, d, k, cpu_iters)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{rows} rows x 5 Lloyd iterations of the same blobs shape (k={k}, d={d}), "
+                        "sample": f"{rows} rows x {cpu_iters} Lloyd iterations of the same blobs shape (k={k}, d={d}), "
                                   f"oracle/kmeans_oracle.c OpenMP fp64, {dt:.1f} s"}
 
     if rank == 0:

@@ -35,10 +35,19 @@ int oracle_num_threads(void) {
  * mind may be NULL. */
 void oracle_assign(const float* X, int64_t n, int d, const float* C, int k,
                    int32_t* labels, double* mind) {
+  /* Centres are processed JB at a time with the centre index as the vector dimension: every (row, centre) dot product is
+   * still the sequential sum over t = 0..d-1 in fp64 (same order, same rounding as a scalar loop), but JB of them run
+   * as independent SIMD lanes, which is what lets the compiler vectorise a reduction it must not re-associate. */
+  enum { JB = 32 };
+  const int kp = (k + JB - 1) / JB * JB;
   double* cn = (double*)malloc(sizeof(double) * (size_t)k);
+  double* Ct = (double*)calloc((size_t)d * kp, sizeof(double)); /* [d][kp], zero padded */
   for (int j = 0; j < k; ++j) {
     double s = 0.0;
-    for (int t = 0; t < d; ++t) s += (double)C[(size_t)j * d + t] * (double)C[(size_t)j * d + t];
+    for (int t = 0; t < d; ++t) {
+      s += (double)C[(size_t)j * d + t] * (double)C[(size_t)j * d + t];
+      Ct[(size_t)t * kp + j] = (double)C[(size_t)j * d + t];
+    }
     cn[j] = s;
   }
 #pragma omp parallel for schedule(static)
@@ -48,17 +57,26 @@ void oracle_assign(const float* X, int64_t n, int d, const float* C, int k,
     for (int t = 0; t < d; ++t) xn += (double)x[t] * (double)x[t];
     double best = DBL_MAX;
     int bj = 0;
-    for (int j = 0; j < k; ++j) {
-      const float* c = C + (size_t)j * d;
-      double dot = 0.0;
-      for (int t = 0; t < d; ++t) dot += (double)x[t] * (double)c[t];
-      double dist = xn + cn[j] - 2.0 * dot;
-      if (dist < 0.0) dist = 0.0;
-      if (dist < best) { best = dist; bj = j; }
+    for (int j0 = 0; j0 < k; j0 += JB) {
+      double dot[JB];
+      for (int jj = 0; jj < JB; ++jj) dot[jj] = 0.0;
+      for (int t = 0; t < d; ++t) {
+        const double xt = (double)x[t];
+        const double* ct = Ct + (size_t)t * kp + j0;
+#pragma omp simd
+        for (int jj = 0; jj < JB; ++jj) dot[jj] += xt * ct[jj];
+      }
+      const int jn = (k - j0 < JB) ? (k - j0) : JB;
+      for (int jj = 0; jj < jn; ++jj) { /* index order, strict '<': lowest index wins ties */
+        double dist = xn + cn[j0 + jj] - 2.0 * dot[jj];
+        if (dist < 0.0) dist = 0.0;
+        if (dist < best) { best = dist; bj = j0 + jj; }
+      }
     }
     labels[i] = bj;
     if (mind) mind[i] = best;
   }
+  free(Ct);
   free(cn);
 }
 
