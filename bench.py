@@ -135,14 +135,29 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def cpu_reference_run(n_rows: int, d: int, k: int, iters: int, seed: int = 1234):
-    """Times the oracle's C/OpenMP Lloyd port (oracle/kmeans_oracle.c) on a bounded sample — CPU baseline only."""
+_CPU_SAMPLE = {}
+
+
+def cpu_sample(n_rows: int, d: int, k: int, seed: int = 1234):
+    """Host blobs of the benchmark's shape (k centres ~ U(-10,10)^d, unit-variance noise), generated once per process."""
     import numpy as np
 
-    from oracle import c_oracle
-    from oracle import kmeans_oracle as ko
+    key = (n_rows, d, k, seed)
+    if key not in _CPU_SAMPLE:
+        rng = np.random.default_rng(seed)
+        centers = rng.uniform(-10.0, 10.0, size=(k, d)).astype(np.float32)
+        X = rng.standard_normal(size=(n_rows, d), dtype=np.float32)
+        X += centers[rng.integers(0, k, size=n_rows)]
+        _CPU_SAMPLE.clear()
+        _CPU_SAMPLE[key] = np.ascontiguousarray(X)
+    return _CPU_SAMPLE[key]
 
-    X, _ = ko.make_blobs(n_rows, d, k, seed=seed)
+
+def cpu_reference_run(n_rows: int, d: int, k: int, iters: int, seed: int = 1234):
+    """Times the oracle's C/OpenMP Lloyd port (oracle/kmeans_oracle.c) on a bounded sample — CPU baseline only."""
+    from oracle import c_oracle
+
+    X = cpu_sample(n_rows, d, k, seed)
     C0 = X[:k].copy()
     c_oracle.lloyd(X[: min(n_rows, 2000)], C0, 1, -1.0, want_labels=False)  # warm the library
     t0 = time.perf_counter()
