@@ -41,6 +41,16 @@ namespace {
 #ifndef B2K_PROBE
 #define B2K_PROBE 0
 #endif
+// Round-2 experiment hooks (default off; untested on hardware until enabled with -D...=1 and A/B-measured):
+//   B2K_EPI_PAR_POLL   the second epilogue warp polls lab_empty while the first polls d_full (one join instead of a
+//                      wait by all four warps at the end of the sort)
+//   B2K_MMA_LANE_POLL  the MMA issuer polls the a_full barriers of a chunk pair with two lanes of one try_wait
+#ifndef B2K_EPI_PAR_POLL
+#define B2K_EPI_PAR_POLL 0
+#endif
+#ifndef B2K_MMA_LANE_POLL
+#define B2K_MMA_LANE_POLL 0
+#endif
 #ifndef B2K_MMA_WAIT
 #define B2K_MMA_WAIT mbar_wait_cluster   // alternative: mbar_spin (CTA-scope test_wait loop; same speed, measured)
 #endif
@@ -367,6 +377,16 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
     if (++spins == (1u << 24)) mbar_timeout(bar, parity);
   }
 }
+// Lane-parallel poll: every lane with active != 0 waits for ITS OWN barrier/parity; one try_wait instruction carries all
+// the addresses, so the (few hundred cycle) cost of a wait is paid once for the whole set.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_lanes(uint32_t my_bar, uint32_t my_parity, bool active) {
+  uint32_t spins = 0;
+  bool ok = !active;
+  while (!__all_sync(0xffffffffu, ok)) {
+    if (!ok) ok = mbar_try_wait(my_bar, my_parity) != 0;
+    if (++spins == (1u << 22)) mbar_timeout(my_bar, my_parity);
+  }
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
@@ -631,8 +651,20 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-        if constexpr (PAIR) B2K_MMA_WAIT(bar(G::B_AFULL + as), aph);
-        else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
+#if B2K_MMA_LANE_POLL
+        // chunk pairs are signalled together (convert CG = 2): lanes 0/1 poll the pair's two a_full barriers at once
+        // when the pair starts; the odd chunk then needs no wait of its own.  (as is even here: NA and NCH are even.)
+        if constexpr (G::NCH % 2 == 0) {
+          if ((c & 1) == 0) {
+            const int my_as = as + (lane & 1);
+            mbar_wait_lanes(bar(G::B_AFULL + my_as), aph, lane < 2);
+          }
+        } else
+#endif
+        {
+          if constexpr (PAIR) B2K_MMA_WAIT(bar(G::B_AFULL + as), aph);
+          else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
+        }
         tc_fence_after();
         if (c == 0) B2K_TR(ti, 14);
         if (c == G::NCH - 2) B2K_TR(ti, 10);
@@ -821,6 +853,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       if (warp == W_EPI0) mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
+#if B2K_EPI_PAR_POLL
+      if (warp == W_EPI0 + 1) mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);   // joined by bar.sync 5
+#endif
       asm volatile("bar.sync 5, 128;" ::: "memory");
       tc_fence_after();
       B2K_T0(t_e0);
@@ -945,7 +980,9 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         for (int q2 = 0; q2 < 3; ++q2)
           if (q2 < q) pos += (int)cnt[q2 * KP + key];
       }
+#if !B2K_EPI_PAR_POLL
       mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
+#endif
       if (valid) rows_sorted[pos] = (uint16_t)(r * 128 + ((r & 7) << 4));
       if (q == 0) {
 #pragma unroll
