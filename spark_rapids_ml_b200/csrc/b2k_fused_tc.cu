@@ -757,8 +757,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         if (warp == W_CONVERT0) { if (c == 0) B2K_TR(ti, 9); if (c + CG >= G::NCH) B2K_TR(ti, 2); }
         // need_cost is hoisted out of the element loop (two copies of the body): a per-float4 branch costs as
         // much issue bandwidth as a fifth of the split itself
-        auto convert_group = [&](auto nc_tag) {
-          constexpr bool NC = decltype(nc_tag)::value;
+        auto convert_group = [&](auto) {
 #pragma unroll 1   // code size (instruction fetch)
         for (int g = 0; g < CG; ++g) {
           const int xsg = (g == 0) ? xs_g[0] : xs_g[CG - 1], asg = (g == 0) ? as_g[0] : as_g[CG - 1];
