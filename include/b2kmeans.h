@@ -82,7 +82,8 @@ typedef enum b2k_layout { B2K_LAYOUT_ROWS = 0, B2K_LAYOUT_COLUMNS = 1 } b2k_layo
 typedef enum b2k_kernel_path {
   B2K_PATH_AUTO = 0,
   B2K_PATH_GENERIC = 1, /* SIMT fp32 tiles: any (k, d) */
-  B2K_PATH_TCGEN05 = 2  /* TMA + tcgen05 3xTF32 fused assign+update; fails with UNSUPPORTED otherwise */
+  B2K_PATH_TCGEN05 = 2  /* TMA + tcgen05 fused assign+update (3xTF32 for k, d <= 128; 1xTF32 screening + exact
+                           recheck for k, d <= 256); fails with UNSUPPORTED otherwise */
 } b2k_kernel_path;
 
 /* Per-fit statistics (b2k_get_stats): what ran, for tests and bench.py's gpu_launches claim. */
@@ -96,6 +97,10 @@ typedef struct b2k_stats {
   double last_fused_ms;        /* mean device time of the fused kernel over the last lloyd call (CUDA events
                                   on the caller's stream; 0 unless option "time_kernels" is 1) */
   double last_loop_ms;         /* device time of the whole last Lloyd loop (same condition) */
+  int64_t recheck_rows;        /* large-shape kernel (k, d <= 256: 1xTF32 screening): rows of the last lloyd/assign call
+                                  whose approximate margin was below the proven error bound and were re-decided
+                                  exactly (summed over its passes; 0 unless option "collect_recheck" is 1) */
+  int64_t recheck_candidates;  /* ... exact candidate distances evaluated for them */
 } b2k_stats;
 
 int b2k_version(void);
@@ -104,7 +109,9 @@ const char* b2k_last_error(const b2k_ctx* ctx);
 int b2k_ctx_create(int device, b2k_ctx** out);
 int b2k_ctx_destroy(b2k_ctx* ctx);
 /* Options: "kernel_path" (b2k_kernel_path), "time_kernels" (0/1), "check_every" (iterations between host
- * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "pair" (1 = use the
+ * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "variant_t" (1 = route every shape with k, d <= 256 through the
+ * large-shape kernel b2k_fused_t.cu; default 0 = only shapes the 3xTF32 kernel does not cover), "collect_recheck"
+ * (1 = lloyd/assign synchronise and fill b2k_stats.recheck_*), "pair" (1 = use the
  * CTA-pair tcgen05 cta_group::2 kernel where instantiated, default 1); diagnostic builds only (`make trace` ->
  * libb2kmeans_trace.so, `-DB2K_PROBE=1`): "profile_fused" (0/1; the product build rejects it with
  * B2K_ERR_UNSUPPORTED at the next fused launch), "probe" (timing experiments that skip work). */

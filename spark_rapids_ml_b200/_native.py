@@ -71,6 +71,8 @@ class Stats(ctypes.Structure):
         ("last_n_iter", ctypes.c_int32),
         ("last_fused_ms", ctypes.c_double),
         ("last_loop_ms", ctypes.c_double),
+        ("recheck_rows", ctypes.c_int64),
+        ("recheck_candidates", ctypes.c_int64),
     ]
 
 

@@ -98,6 +98,10 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->pf_dist = (int)value;
   } else if (k == "pair") {
     ctx->pair = value ? 1 : 0;
+  } else if (k == "variant_t") {
+    ctx->force_variant_t = value ? 1 : 0;
+  } else if (k == "collect_recheck") {
+    ctx->collect_recheck = value ? 1 : 0;
   } else if (k == "profile_fused") {
     ctx->profile_fused = value ? 1 : 0;
   } else if (k == "grid_limit") {
@@ -252,6 +256,8 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
     B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
   }
 
+  if (fused && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, B.plan, B.plan_scratch, X, n, d, k, s));
+
   int launched = 0;
   bool done = (max_iter == 0);
   while (!done && launched < max_iter) {
@@ -273,13 +279,13 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
         float* partials;
         int32_t* counts;
         double* cost_partials;
-        b2k_fused_views(B.plan, B.plan_scratch, k, d, &partials, &counts, &cost_partials);
-        B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.grid, k, d, B.R, B.st, s));
+        b2k_fused_views(B.plan, B.plan_scratch, n, k, d, &partials, &counts, &cost_partials);
+        B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.P, B.plan.grid, k, d, B.R, B.st, s));
       } else {
         B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
         B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, B.cnorm, k, B.labels, nullptr, B.st, s));
         B2K_TRY(b2k_launch_update_generic(ctx, X, n, d, B.labels, k, B.P, B.partials, B.counts, B.st, s));
-        B2K_TRY(b2k_launch_reduce_partials(ctx, B.partials, B.counts, nullptr, B.P, k, d, B.R, B.st, s));
+        B2K_TRY(b2k_launch_reduce_partials(ctx, B.partials, B.counts, nullptr, B.P, 0, k, d, B.R, B.st, s));
       }
       if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, B.R, rlen, s));
       B2K_TRY(b2k_launch_finalize(ctx, B.R, C, k, d, B.shift_scratch, B.st, s));
@@ -313,6 +319,12 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
     cudaEventDestroy(loop1);
   }
   ctx->stats.last_n_iter = ctx->h_state->iter;
+  if (fused && ctx->collect_recheck && max_iter > 0) {
+    unsigned long long rs[2];
+    B2K_TRY(b2k_fused_recheck_stats(ctx, B.plan, B.plan_scratch, n, k, d, rs, s));
+    ctx->stats.recheck_rows = (int64_t)rs[0];
+    ctx->stats.recheck_candidates = (int64_t)rs[1];
+  }
   if (n_iter_out) *n_iter_out = ctx->h_state->iter;
   if (shift_out) *shift_out = ctx->h_state->shift;
   return B2K_OK;
@@ -345,14 +357,22 @@ static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const flo
       return b2k_fail(ctx, B2K_ERR_STATE, "assign_impl: scratch must be pre-reserved by the caller");
     B2K_TRY(b2k_scratch_reserve(ctx, need));
     void* ps = static_cast<char*>(ctx->scratch) + align_up(scratch_off, 1024);
+    B2K_TRY(b2k_fused_prepare(ctx, plan, ps, X, n, d, k, s));
+    ctx->want_cost = cost_dev != nullptr ? 1 : 0;
     B2K_TRY(b2k_launch_fused(ctx, plan, ps, X, n, d, C, k, labels, mindist, false, nullptr, s));
     if (cost_dev) {
       float* partials;
       int32_t* counts;
       double* cost_partials;
-      b2k_fused_views(plan, ps, k, d, &partials, &counts, &cost_partials);
+      b2k_fused_views(plan, ps, n, k, d, &partials, &counts, &cost_partials);
       // fold the per-CTA cost partials in index order
       B2K_TRY(b2k_launch_fold_f64(ctx, cost_partials, plan.grid, cost_dev, s));
+    }
+    if (ctx->collect_recheck) {
+      unsigned long long rs[2];
+      B2K_TRY(b2k_fused_recheck_stats(ctx, plan, ps, n, k, d, rs, s));
+      ctx->stats.recheck_rows = (int64_t)rs[0];
+      ctx->stats.recheck_candidates = (int64_t)rs[1];
     }
   } else {
     const int nblocks = 1024;

@@ -322,11 +322,11 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
 }
 
 int b2k_launch_reduce_partials(b2k_ctx* ctx, const float* partials, const int32_t* counts,
-                               const double* cost_partials, int P, int k, int d, double* R,
+                               const double* cost_partials, int P, int Pc, int k, int d, double* R,
                                const B2kLoopState* st, cudaStream_t s) {
   size_t len = b2k_reduced_len(k, d);
   unsigned blocks = (unsigned)((len + 255) / 256);
-  k_reduce_partials<<<blocks, 256, 0, s>>>(partials, counts, P, cost_partials, P, k, d, R, st);
+  k_reduce_partials<<<blocks, 256, 0, s>>>(partials, counts, P, cost_partials, Pc, k, d, R, st);
   ctx->stats.kernel_launches++;
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;

@@ -40,6 +40,9 @@ struct b2k_ctx {
   int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
   int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
   int pf_dist = -1;              // option "pf_dist": accepted, ignored (the L2 prefetch experiment was removed)
+  int force_variant_t = 0;       // option "variant_t": route every supported shape through b2k_fused_t.cu (tests)
+  int collect_recheck = 0;       // option "collect_recheck": fill stats.recheck_* (costs a stream sync per call)
+  int want_cost = 1;             // assign passes: compute the cost partial (set by assign_impl)
   int profile_fused = 0;         // record per-role blocked-cycle counters of the fused kernel
   long long* prof_dev = nullptr;  // [grid][18 warps][8]
   int prof_grid = 0;
@@ -101,7 +104,7 @@ int b2k_launch_update_generic(b2k_ctx* ctx, const float* X, int64_t n, int d, co
                               cudaStream_t s);
 // R[k*d+k+1] (double) = fixed-order sum over P partials (+ cost from mindist partial sums)
 int b2k_launch_reduce_partials(b2k_ctx* ctx, const float* partials, const int32_t* counts,
-                               const double* cost_partials, int P, int k, int d, double* R,
+                               const double* cost_partials, int P, int Pc, int k, int d, double* R,
                                const B2kLoopState* st, cudaStream_t s);
 // C <- R.S / R.w (w == 0 keeps C), shift, iter++, done.  shift_scratch: k doubles.
 int b2k_launch_finalize(b2k_ctx* ctx, const double* R, float* C, int k, int d, double* shift_scratch,
@@ -127,18 +130,39 @@ struct B2kFusedPlan {
   int KP = 0, DP = 0;        // padded cluster count / dimension of the instantiation, 0 = unsupported
   int grid = 0;              // persistent CTAs
   int pair = 0;              // 1: CTA-pair (tcgen05 cta_group::2) instantiation, grid is even
-  size_t scratch_bytes = 0;  // Chi/Clo/cnorm + partials/counts/cost
+  int variant = 0;           // 0: b2k_fused_tc.cu (k <= 128, d <= 128, 3xTF32); 1: b2k_fused_t.cu (k, d <= 256, 1xTF32 + recheck)
+  int P = 0;                 // partial-sum slots the pass writes (variant 0: grid, variant 1: grid / 2 = CTA pairs)
+  size_t scratch_bytes = 0;  // centre operands/cnorm + partials/counts/cost (+ row norms, variant 1)
 };
 bool b2k_fused_supported(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X);
 int b2k_fused_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan);
+// Once per fit / lloyd / assign call, before the first b2k_launch_fused on this X (variant 1: row norms; variant 0: no-op)
+int b2k_fused_prepare(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d, int k,
+                      cudaStream_t s);
 // One fused pass: (labels_out, mindist_out optional) + partial sums/counts/cost into plan scratch.
 // `do_update` = accumulate partial sums (Lloyd iteration) or labels only (assign/inertia pass).
 int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X,
                      int64_t n, int d, const float* C, int k, int32_t* labels_out, float* mindist_out,
                      bool do_update, const B2kLoopState* st, cudaStream_t s, const double* prev_counts = nullptr);
 // Views into the plan scratch after a fused pass (to feed b2k_launch_reduce_partials)
-void b2k_fused_views(const B2kFusedPlan& plan, void* plan_scratch, int k, int d, float** partials,
+void b2k_fused_views(const B2kFusedPlan& plan, void* plan_scratch, int64_t n, int k, int d, float** partials,
                      int32_t** counts, double** cost_partials);
+// variant 1 diagnostics: {rows re-decided exactly, candidate distances evaluated} since the last b2k_fused_prepare
+int b2k_fused_recheck_stats(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, int64_t n, int k, int d,
+                            unsigned long long out[2], cudaStream_t s);
+
+// b2k_fused_t.cu (variant 1)
+bool b2k_fused_t_supported(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X);
+int b2k_fused_t_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan);
+void b2k_fused_t_views(const B2kFusedPlan& plan, void* plan_scratch, int64_t n, int k, int d, float** partials,
+                       int32_t** counts, double** cost_partials, unsigned long long** rstat);
+int b2k_fused_t_prepare(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d,
+                        int k, cudaStream_t s);
+int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d,
+                       const float* C, int k, int32_t* labels_out, float* mindist_out, bool do_update, bool need_cost,
+                       const B2kLoopState* st, cudaStream_t s, const double* prev_counts);
+int b2k_fused_encode_2d(b2k_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int l2_256);
 
 // ------------------------------------------------------------------------------------------------
 // comm — b2k_comm.cu
