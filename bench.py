@@ -40,6 +40,10 @@ def parse_args():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--n-per-gpu", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--kernel-path", default="auto", choices=["auto", "generic", "tcgen05"])
+    ap.add_argument("--init", default="first_k", choices=["first_k", "near_true"],
+                    help="initial centres of the timed Lloyd loop: the first k rows of rank 0, or the generating "
+                         "centres + 0.25 sigma noise (what a k-means|| start looks like on separated blobs)")
+    ap.add_argument("--probe", type=int, default=0, help="diagnostic builds only (B2K_LIB=libb2kmeans_probe.so)")
     ap.add_argument("--e2e-iters", type=int, default=20, help="maxIter of the end-to-end fit (Spark default 20)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -225,6 +229,8 @@ def main():
 
     ctx = _native.Context(local_rank)
     ctx.set_option("kernel_path", {"auto": 0, "generic": 1, "tcgen05": 2}[args.kernel_path])
+    if args.probe:
+        ctx.set_option("probe", args.probe)
     if world > 1:
         uid = torch.zeros(_native.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -242,7 +248,11 @@ def main():
         e = min(n_local, s + chunk)
         z = torch.randint(0, k, (e - s,), generator=g, device=dev)
         X[s:e] = centers_true[z] + torch.randn((e - s, d), generator=g, device=dev)
-    C0 = X[:k].clone()
+    if args.init == "near_true":
+        g0 = torch.Generator(device=dev).manual_seed(7)
+        C0 = (centers_true + 0.25 * torch.randn((k, d), generator=g0, device=dev)).contiguous()
+    else:
+        C0 = X[:k].clone()
     if world > 1:
         dist.broadcast(C0, 0)  # deterministic "array" init = first k rows of rank 0
 
@@ -264,6 +274,7 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.set_option("time_kernels", 1)   # CUDA events around every fused launch of THIS timed loop (roofline below)
+    ctx.set_option("collect_recheck", 1)
     e0.record()
     n_iter, shift = ctx.kmeans_lloyd(X, C, args.steps, -1.0)
     e1.record()
@@ -293,7 +304,9 @@ def main():
                     "kernel_ms": st2["last_fused_ms"], "loop_ms_per_iter": st2["last_loop_ms"] / max(1, st2["last_n_iter"]),
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "tensor_flops_per_launch": 2.0 * n_local * d * k,
-                    "tensor_tflops_1x": 2.0 * n_local * d * k / (st2["last_fused_ms"] / 1e3) / 1e12}
+                    "tensor_tflops_1x": 2.0 * n_local * d * k / (st2["last_fused_ms"] / 1e3) / 1e12,
+                    "recheck_rows_per_iter": st2["recheck_rows"] / max(1, st2["last_n_iter"]),
+                    "recheck_candidates_per_iter": st2["recheck_candidates"] / max(1, st2["last_n_iter"])}
     else:
         # generic path: time one assign+update iteration as a whole
         roofline = {"bound": "hbm", "kernel": "generic assign+update (2 passes over X)", "achieved":

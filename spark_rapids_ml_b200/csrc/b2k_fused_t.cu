@@ -37,6 +37,24 @@ namespace {
 #ifndef B2K_MMA_WAIT
 #define B2K_MMA_WAIT mbar_wait_cluster
 #endif
+// -DB2K_PROBE=1 (make probe -> libb2kmeans_probe.so): option "probe" skips one stage's work (WRONG results; timing only):
+//   1 update rows   2 epilogue D processing   3 epilogue exchange   4 MMAs   5 sort   6 remote rows read locally
+#ifndef B2K_PROBE
+#define B2K_PROBE 0
+#endif
+#if B2K_PROBE
+#define B2K_PROBE_IS(x) (args.probe == (x))
+// event trace (option "profile_fused"): clock64 of 16 events x 8 steps (20..27) of CTAs 0 and 1, read back through
+// b2k_get_fused_profile: [cta][step][event]
+#define B2K_TR(itv, ev)                                                                                   \
+  do {                                                                                                    \
+    if (args.trace != nullptr && blockIdx.x < 2 && (itv) >= 20 && (itv) < 28 && (threadIdx.x & 31) == 0) \
+      args.trace[((int)blockIdx.x * 8 + ((itv)-20)) * 16 + (ev)] = clock64();                             \
+  } while (0)
+#else
+#define B2K_PROBE_IS(x) false
+#define B2K_TR(itv, ev) ((void)0)
+#endif
 #include "b2k_ptx.cuh"
 
 constexpr int TN = 128;                      // X rows per step = UMMA N (64 per CTA of the pair)
@@ -64,29 +82,32 @@ constexpr int NTHREADS = NWARPS * 32;
 constexpr int OFF_RING = 0;
 constexpr int OFF_PART = NSLOT * SLOT_BYTES;            // uint2 part[2][8 sources][128 columns]: (best, second) keys
 constexpr int OFF_LAB = OFF_PART + 2 * 8 * TN * 8;      // int32 lab[2][128]: final labels of the step
-constexpr int OFF_CAND = OFF_LAB + 2 * TN * 4;          // u32 cand[128][8]: candidate bit masks of flagged rows
-constexpr int OFF_CANDT = OFF_CAND + TN * 8 * 4;        // f32 candT[128]: best + thr per column
-constexpr int OFF_FIN = OFF_CANDT + TN * 4;             // int32 fin[128]: rechecked labels
-constexpr int OFF_SORT = OFF_FIN + TN * 4;              // counting-sort scratch, see SortT
+constexpr int OFF_CAND = OFF_LAB + 2 * TN * 4;          // u32 cand[128][4]: candidate bit masks (this CTA's clusters)
+constexpr int OFF_CANDT = OFF_CAND + TN * 4 * 4;        // f32 candT[128]: best + thr per column
+constexpr int OFF_RES = OFF_CANDT + TN * 4;             // uint2 res[128]: this CTA's exact partial winner (value, cluster)
+constexpr int OFF_RESP = OFF_RES + TN * 8;              // uint2 resp[128]: the peer's (st.async)
+constexpr int OFF_XOFF = OFF_RESP + TN * 8;             // f32 xoff[128]: per-row key offset ||x||^2 + thr
+constexpr int OFF_FLIST = OFF_XOFF + TN * 4;            // u8 flist[128]: flagged columns of the step
+constexpr int OFF_CNORM = OFF_FLIST + TN;               // f32 cnorm[256]: ||c||^2 of every centre (exact recheck)
+constexpr int OFF_SORT = OFF_CNORM + 256 * 4;           // cluster <-> update-warp key tables, see SortT
 struct SortT {
-  static constexpr int CNT = 0;                         // u8 [2][4][128] per-warp key histograms
-  static constexpr int ROWS = CNT + 2 * 4 * KH;         // u16 [2][128] sorted row entries
-  static constexpr int START = ROWS + 2 * TN * 2;       // u8 [2][144] exclusive start per key (+ total)
-  static constexpr int KEYTAB = START + 2 * 144;        // u8 [256] cluster -> key (cta*128 + warp*8 + slot)
+  static constexpr int KEYTAB = 0;                      // u8 [256] cluster -> key (cta*128 + warp*8 + slot)
   static constexpr int KEYINV = KEYTAB + 256;           // u8 [256] key -> cluster
   static constexpr int BYTES = KEYINV + 256;
 };
 constexpr int OFF_MISC = (OFF_SORT + SortT::BYTES + 15) & ~15;   // flag words [4] u32, tmem ptr, cost doubles [16]
-constexpr int MISC_FLAGW = 0, MISC_TMEMPTR = 16, MISC_COST = 32;
-constexpr int OFF_BARS = OFF_MISC + 32 + 16 * 8;
+constexpr int MISC_FLAGW = 0, MISC_TMEMPTR = 32, MISC_COST = 48;
+constexpr int OFF_BARS = OFF_MISC + 48 + 16 * 8;
 constexpr int B_XFULL = 0;                   // [NSLOT] leader CTA only: both CTAs' TMA boxes of a chunk landed
 constexpr int B_SFREE = B_XFULL + NSLOT;     // [8] step slot may be overwritten (local + remote update roles done)
 constexpr int B_DFULL = B_SFREE + 8;         // [2]
 constexpr int B_DEMPTY = B_DFULL + 2;        // [2] leader CTA only, count 2
-constexpr int B_EX = B_DEMPTY + 2;           // [1] epilogue exchange (count 2: one arrival per CTA)
-constexpr int B_LFULL = B_EX + 1;            // [2]
+constexpr int B_RX = B_DEMPTY + 2;           // [1] the peer's exact partial winners of a recheck landed (st.async complete_tx)
+constexpr int B_LFULL = B_RX + 1;            // [2]
 constexpr int B_LEMPTY = B_LFULL + 2;        // [2]
-constexpr int NBARS = B_LEMPTY + 2;
+constexpr int B_PX = B_LEMPTY + 2;           // [2] the peer's partial keys of a step landed here (st.async complete_tx)
+constexpr int NBARS = B_PX + 2;
+constexpr uint32_t PX_BYTES = 4u * (TN / 32) * 32u * 8u;   // 4 warps x 4 chunks x 32 lanes x 8 bytes per step
 constexpr int SMEM_BYTES = OFF_BARS + NBARS * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 
@@ -112,6 +133,17 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr_cluster, uint32_t a,
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr_cluster, uint32_t a) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr_cluster), "r"(a) : "memory");
 }
+// remote store that itself signals the destination CTA's mbarrier (complete_tx): no release fence on the producer side
+__device__ __forceinline__ void st_async_v2(uint32_t addr_cluster, uint32_t a, uint32_t b, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr_cluster),
+               "r"(a), "r"(b), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t addr_cluster, uint32_t a, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr_cluster), "r"(a),
+               "r"(bar_cluster)
+               : "memory");
+}
 __device__ __forceinline__ void ld_cluster_2(uint32_t addr_cluster, uint64_t& a, uint64_t& b) {
   asm volatile("ld.shared::cluster.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr_cluster));
 }
@@ -136,56 +168,45 @@ __device__ __forceinline__ void mbar_wait_cluster_nocall(uint32_t bar, uint32_t 
   }
 }
 
-// (dist, cluster) -> one ordered key: float bits mapped to an unsigned integer with the same order, low 8 bits replaced
-// by the cluster index.  Costs 2^-15 relative resolution of dist (part of the proven bound, k_tables_t).
-__device__ __forceinline__ uint32_t pack_key(float dist, uint32_t j) {
-  const uint32_t u = __float_as_uint(dist);
-  const uint32_t s = (uint32_t)((int32_t)u >> 31) | 0x80000000u;
-  return ((u ^ s) & 0xffffff00u) | j;
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
-__device__ __forceinline__ float unpack_key(uint32_t key) {
-  const uint32_t u = key & 0xffffff00u;
-  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr_cluster) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr_cluster));
+  return v;
 }
-// merge two (smallest, second smallest) pairs
+
+// Keys: (dist' + ||x||^2 + thr) is a positive float, so its bits order like an unsigned integer; the low 8 bits carry the
+// cluster index (2^-15 relative resolution of the key value, part of the proven bound in k_tables_t).
+// merge two (smallest, second smallest) pairs of disjoint key sets
 __device__ __forceinline__ void merge2(uint32_t& a1, uint32_t& a2, uint32_t b1, uint32_t b2) {
   const uint32_t lo = min(a1, b1), hi = max(a1, b1);
   a2 = min(hi, min(a2, b2));
   a1 = lo;
 }
-
-// Transposing butterfly: on entry every lane holds the keys of ITS cluster for 32 columns; on exit lane c holds the
-// smallest and second smallest key of column c over the 32 clusters of the warp.
-template <int N>
-__device__ __forceinline__ void bfly_level(uint32_t (&m1)[16], uint32_t (&m2)[16], int lane) {
-  const bool hi = (lane & N) != 0;
+// One level of the transposing butterfly over lane bit LM: on entry a lane holds 2 N columns, on exit the N columns whose
+// index bit matches its lane bit, reduced over the lane pair.
+template <int N, int LM>
+__device__ __forceinline__ void bfly2_level(uint32_t (&m1)[8], uint32_t (&m2)[8], int lane) {
+  const bool hi = (lane & LM) != 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const uint32_t s1 = hi ? m1[i] : m1[i + N], s2 = hi ? m2[i] : m2[i + N];
     uint32_t k1 = hi ? m1[i + N] : m1[i], k2 = hi ? m2[i + N] : m2[i];
-    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, s1, N), r2 = __shfl_xor_sync(0xffffffffu, s2, N);
+    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, s1, LM), r2 = __shfl_xor_sync(0xffffffffu, s2, LM);
     merge2(k1, k2, r1, r2);
     m1[i] = k1;
     m2[i] = k2;
   }
-}
-__device__ __forceinline__ void bfly32(const uint32_t (&v)[32], int lane, uint32_t& o1, uint32_t& o2) {
-  uint32_t m1[16], m2[16];
-  const bool hi = (lane & 16) != 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t send = hi ? v[i] : v[i + 16];
-    const uint32_t keep = hi ? v[i + 16] : v[i];
-    const uint32_t r = __shfl_xor_sync(0xffffffffu, send, 16);
-    m1[i] = min(keep, r);
-    m2[i] = max(keep, r);
-  }
-  bfly_level<8>(m1, m2, lane);
-  bfly_level<4>(m1, m2, lane);
-  bfly_level<2>(m1, m2, lane);
-  bfly_level<1>(m1, m2, lane);
-  o1 = m1[0];
-  o2 = m2[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,6 +318,8 @@ struct TArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int need_cost;
+  int probe;
+  long long* trace;
   unsigned long long* rstat;   // [2] rechecked rows, candidates evaluated (diagnostics) or NULL
   const B2kLoopState* st;
 };
@@ -319,10 +342,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
   const uint32_t bars = base + OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
   uint2* part_s = reinterpret_cast<uint2*>(gbase + OFF_PART);
+  float* xoff_s = reinterpret_cast<float*>(gbase + OFF_XOFF);
   int32_t* lab_s = reinterpret_cast<int32_t*>(gbase + OFF_LAB);
   uint32_t* cand_s = reinterpret_cast<uint32_t*>(gbase + OFF_CAND);
   float* candT_s = reinterpret_cast<float*>(gbase + OFF_CANDT);
-  int32_t* fin_s = reinterpret_cast<int32_t*>(gbase + OFF_FIN);
+  uint2* res_s = reinterpret_cast<uint2*>(gbase + OFF_RES);
+  const uint2* resp_s = reinterpret_cast<const uint2*>(gbase + OFF_RESP);
+  uint8_t* flist_s = gbase + OFF_FLIST;
+  float* cnorm_s = reinterpret_cast<float*>(gbase + OFF_CNORM);
   uint8_t* sort_s = gbase + OFF_SORT;
   uint8_t* keytab_s = sort_s + SortT::KEYTAB;
   uint8_t* keyinv_s = sort_s + SortT::KEYINV;
@@ -339,14 +366,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&mapX);
     for (int i = 0; i < NSLOT; ++i) mbar_init(bar(B_XFULL + i), 1);
-    for (int i = 0; i < 8; ++i) mbar_init(bar(B_SFREE + i), 2);
+    for (int i = 0; i < 8; ++i) mbar_init(bar(B_SFREE + i), 2 * N_UPD);   // every update warp of both CTAs
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(B_DFULL + i), 1);
       mbar_init(bar(B_DEMPTY + i), 2);
       mbar_init(bar(B_LFULL + i), 1);
-      mbar_init(bar(B_LEMPTY + i), 1);
+      mbar_init(bar(B_LEMPTY + i), N_UPD);
     }
-    mbar_init(bar(B_EX), 2);
+    mbar_init(bar(B_RX), 1);
+    mbar_init(bar(B_PX + 0), 1);
+    mbar_init(bar(B_PX + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
@@ -356,6 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   for (int j = threadIdx.x; j < 256; j += NTHREADS) {
+    cnorm_s[j] = args.cnorm[j];
     keytab_s[j] = args.keytab[j];
     keyinv_s[j] = args.keyinv[j];
   }
@@ -408,24 +438,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
 #pragma unroll
       for (int i = 0; i < UPL; ++i) acc[c][i][0] = acc[c][i][1] = 0ull;
     }
-    const uint32_t sfree_peer0 = mapa_u32(bar(B_SFREE), peer);
     const uint32_t unit_js = (uint32_t)(lane & 7) << 4;
+    const int k0 = (int)rank * KH + u * CPW;   // this warp's key range [k0, k0 + CPW)
     double cost = 0.0;
     for (int it = 0; it < nit; ++it) {
       const int b = it & 1;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int ss = it % NSTEP;
-      if (u == 0) mbar_wait_nocall(bar(B_LFULL + b), bph);
-      asm volatile("bar.sync 2, 512;" ::: "memory");
+      // The update warps run decoupled (no per-step barrier among them): rows per warp and step are Poisson(4), and a
+      // barrier would make every step wait for its most loaded warp (measured: 5-7 k cycles per step against 2.5 k mean).
+      mbar_wait_nocall(bar(B_LFULL + b), bph);
+      if (u == 0) B2K_TR(it, 11);
       // The x_full phases of this step completed before the MMA consumed the slots, which happens-before the
       // commit, the epilogue and hence lab_full: the rows are in shared memory (both CTAs).
       const uint32_t slot0 = ring + (uint32_t)((ss * NCH + (lane >> 3)) * SLOT_BYTES);
       if constexpr (UPD) {
-        const uint16_t* rows_sorted = reinterpret_cast<const uint16_t*>(sort_s + SortT::ROWS) + b * TN;
-        const uint8_t* start = sort_s + SortT::START + b * 144;
-        auto load_row = [&](uint32_t e, uint64_t (&v)[UPL][2]) {
-          const uint32_t a0 = slot0 + ((e & 0x7fffu) ^ unit_js);
-          if ((e >> 15) == rank) {
+        // this warp's rows of the step: labels whose key (cluster -> update warp table) lies in [k0, k0 + 8); processed in
+        // column order with two rows in flight whatever their clusters (a fixed function of the labels: deterministic)
+        uint32_t keyp = 0, vmask = 0;   // per lane: keys of columns lane + 32 sx (one byte each), validity bits
+#pragma unroll
+        for (int sx = 0; sx < 4; ++sx) {
+          const int lab = lab_s[b * TN + sx * 32 + lane];
+          if (lab >= 0) {
+            keyp |= (uint32_t)keytab_s[lab] << (8 * sx);
+            vmask |= 1u << sx;
+          }
+        }
+        auto load_row = [&](int colr, uint64_t (&v)[UPL][2]) {
+          const int lrow = colr & 63;
+          const uint32_t a0 = slot0 + (((uint32_t)(lrow * 128 + ((lrow & 7) << 4))) ^ unit_js);
+          if ((uint32_t)(colr >> 6) == rank || B2K_PROBE_IS(6)) {
 #pragma unroll
             for (int i = 0; i < UPL; ++i) lds128_2(a0 + (uint32_t)(i * 4 * SLOT_BYTES), v[i][0], v[i][1]);
           } else {
@@ -434,34 +476,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
             for (int i = 0; i < UPL; ++i) ld_cluster_2(r0 + (uint32_t)(i * 4 * SLOT_BYTES), v[i][0], v[i][1]);
           }
         };
-        const int sv = (lane <= CPW) ? (int)start[u * CPW + lane] : 0;
-        cnt += __shfl_down_sync(0xffffffffu, sv, 1) - sv;   // meaningful in lanes < CPW
-#pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-          const int i0 = __shfl_sync(0xffffffffu, sv, c);
-          const int i1 = __shfl_sync(0xffffffffu, sv, c + 1);
+        auto add_row = [&](int c, const uint64_t (&v)[UPL][2]) {
+          switch (c) {
+#define B2K_ADD_CASE(C_)                                        \
+  case C_:                                                      \
+    _Pragma("unroll") for (int k2 = 0; k2 < UPL; ++k2) {        \
+      acc[C_][k2][0] = add2(acc[C_][k2][0], v[k2][0]);          \
+      acc[C_][k2][1] = add2(acc[C_][k2][1], v[k2][1]);          \
+    }                                                           \
+    break;
+            B2K_ADD_CASE(0) B2K_ADD_CASE(1) B2K_ADD_CASE(2) B2K_ADD_CASE(3)
+            B2K_ADD_CASE(4) B2K_ADD_CASE(5) B2K_ADD_CASE(6) B2K_ADD_CASE(7)
+#undef B2K_ADD_CASE
+            default: break;
+          }
+        };
+        // two rows in flight: the load of row i + 1 is issued before row i is added (its latency — 30 cycles local,
+        // several hundred through DSMEM under load — is the cost of a row; measured ~700-1000 cycles per row serial)
+        uint64_t vA[UPL][2], vB[UPL][2];
+        if (u == 0) B2K_TR(it, 1);
+        int pend = 0, cP = 0;   // pend: 0 nothing in flight, 1 = vA, 2 = vB (the buffers alternate: no register copies)
 #pragma unroll 1
-          for (int i = i0; i < i1; i += 2) {
-            const bool two = (i + 1 < i1);
-            const uint32_t e0 = rows_sorted[i];
-            const uint32_t e1 = rows_sorted[two ? i + 1 : i];
-            uint64_t v0[UPL][2], v1[UPL][2];
-            load_row(e0, v0);
-            load_row(e1, v1);
-#pragma unroll
-            for (int k2 = 0; k2 < UPL; ++k2) {
-              acc[c][k2][0] = add2(acc[c][k2][0], v0[k2][0]);
-              acc[c][k2][1] = add2(acc[c][k2][1], v0[k2][1]);
+        for (int sx = 0; sx < 4; ++sx) {
+          uint32_t m = __ballot_sync(0xffffffffu, ((vmask >> sx) & 1u) != 0u &&
+                                                       (((keyp >> (8 * sx)) & 255u) - (uint32_t)k0) < (uint32_t)CPW);
+          if (B2K_PROBE_IS(1)) m = 0u;
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int cc = (int)((__shfl_sync(0xffffffffu, keyp, bit) >> (8 * sx)) & 255u) - (k0 & 255);
+            if (lane == cc) ++cnt;
+            if (pend == 0) {
+              load_row(sx * 32 + bit, vA);
+              pend = 1;
+            } else if (pend == 1) {
+              load_row(sx * 32 + bit, vB);
+              add_row(cP, vA);
+              pend = 2;
+            } else {
+              load_row(sx * 32 + bit, vA);
+              add_row(cP, vB);
+              pend = 1;
             }
-            if (two) {
-#pragma unroll
-              for (int k2 = 0; k2 < UPL; ++k2) {
-                acc[c][k2][0] = add2(acc[c][k2][0], v1[k2][0]);
-                acc[c][k2][1] = add2(acc[c][k2][1], v1[k2][1]);
-              }
-            }
+            cP = cc;
           }
         }
+        if (pend == 1) add_row(cP, vA);
+        else if (pend == 2) add_row(cP, vB);
       } else if (args.need_cost) {
         // exact min distance of this CTA's own rows: sum_t (x_t - c_t)^2 against the row's (final) centre
 #pragma unroll 1
@@ -491,11 +552,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
           }
         }
       }
-      asm volatile("bar.sync 3, 512;" ::: "memory");
-      if (u == 0 && lane == 0) {
+      __syncwarp();
+      if (u == 0) B2K_TR(it, 12);
+      if (lane == 0) {
+        // the rows were consumed (their values fed the adds above) before these arrivals: relaxed is enough for the
+        // write-after-read hand-back of the slots to the TMA producers of both CTAs
         mbar_arrive(bar(B_LEMPTY + b));
-        asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar(B_SFREE + ss)) : "memory");
-        mbar_arrive_release_cluster(sfree_peer0 + 8u * (uint32_t)ss);
+        mbar_arrive(bar(B_SFREE + ss));
+        mbar_arrive_cluster(bar(B_SFREE + ss), peer);
       }
     }
     if constexpr (UPD) {
@@ -532,6 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const int ss = it % NSTEP;
       const uint32_t sph = (uint32_t)(it / NSTEP) & 1u;
       mbar_wait_cluster_nocall(bar(B_SFREE + ss), sph ^ 1u);   // acquire.cluster: the peer's update role read this slot
+      B2K_TR(it, 0);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int slot = ss * NCH + c;
@@ -553,76 +618,118 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const uint32_t sph = (uint32_t)(it / NSTEP) & 1u;
       mbar_wait_cluster_nocall(bar(B_DEMPTY + b), bph ^ 1u);
       tc_fence_after();
+      B2K_TR(it, 2);
       const uint32_t d_tmem = tmem_base + D_OFF + b * TN;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int slot = ss * NCH + c;
         mbar_wait_cluster_nocall(bar(B_XFULL + slot), sph);
         tc_fence_after();
+        if (c == 0) B2K_TR(it, 3);
+        if (c == NCH - 1) B2K_TR(it, 14);
         if (elect_one()) {
           const uint32_t bx = ring + slot * SLOT_BYTES;
 #pragma unroll
           for (int ks = 0; ks < CHUNK / 8; ++ks)
-            tc_mma_ts_tf32_pair(d_tmem, tmem_base + (uint32_t)(c * CHUNK + ks * 8), make_kmajor_sw128_desc(bx + ks * 32),
+            if ((!B2K_PROBE_IS(4) || (c | ks) == 0) && (!B2K_PROBE_IS(7) || ks == 0) && (!B2K_PROBE_IS(8) || ks < 2))
+              tc_mma_ts_tf32_pair(d_tmem, tmem_base + (uint32_t)(c * CHUNK + ks * 8), make_kmajor_sw128_desc(bx + ks * 32),
                                 idesc, (c | ks) != 0 ? 1u : 0u);
           if (c == NCH - 1) tc_commit_pair(bar(B_DFULL + b));
         }
         __syncwarp();
       }
+      B2K_TR(it, 4);
     }
    }
   } else if (warp < W_UPD0) {
     // ======================= epilogue warps: D -> keys -> (best, second) -> labels =======================
+    // tcgen05.ld.16x256b hands thread (t0 = lane & 3, t1 = lane >> 2) the TMEM lanes t1 and t1 + 8 of a 16-lane half and
+    // the columns 8 r + 2 t0 + {0, 1}: with both halves a thread owns 4 clusters x 8 columns of a 32-column chunk, reduces
+    // its 4 clusters in registers and only 3 shuffle levels (over t1) remain.
     const int w = warp - W_EPI0;
     const int col = w * 32 + lane;                      // the column (row of the step) this thread combines
-    const uint32_t j = rank * KH + (uint32_t)col;       // the cluster of this thread's TMEM lane
-    const uint32_t lane_field = (uint32_t)(w * 32) << 16;
-    const float cn = args.cnorm[j];
+    const int t0 = lane & 3, t1 = lane >> 2;
+    const uint32_t jid0 = rank * KH + (uint32_t)(w * 32 + t1);   // + 16 h + 8 e: the 4 clusters of this thread
+    float cn4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cn4[q] = args.cnorm[jid0 + 8 * q];   // q = 2 h + e
+    const float cn_lane = args.cnorm[rank * KH + (uint32_t)col];     // 32x32b view (candidate enumeration)
+    const int cidx = (lane & 24) | ((lane & 3) << 1) | ((lane >> 2) & 1);   // column of the chunk this lane ends up with
     const float thrA = args.thr[0], thrB = args.thr[1];
-    const uint32_t part_local0 = base + OFF_PART;
-    const uint32_t part_peer0 = mapa_u32(part_local0, peer);
-    const uint32_t ex_peer = mapa_u32(bar(B_EX), peer);
+    const uint32_t part_peer0 = mapa_u32(base + OFF_PART, peer);
+    const uint32_t resp_peer0 = mapa_u32(base + OFF_RESP, peer);
+    const uint32_t px_peer0 = mapa_u32(bar(B_PX), peer);
+    const uint32_t rx_peer = mapa_u32(bar(B_RX), peer);
     const uint32_t dempty_leader = mapa_u32(bar(B_DEMPTY), 0u);
-    uint32_t exph = 0;
+    const uint32_t src = rank * 4u + (uint32_t)w;
+    uint32_t rxph = 0;
     unsigned long long n_flag = 0, n_cand = 0;
-    // one exchange: everything this CTA's epilogue stored (locally and into the peer) is visible to both afterwards
-    auto exchange = [&]() {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar(B_EX)) : "memory");
-        mbar_arrive_release_cluster(ex_peer);
-      }
-      if (w == 0) mbar_wait_cluster(bar(B_EX), exph);
-      exph ^= 1u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    };
+    float xn_next = 0.f;
+    if (nit > 0) {
+      const int64_t g0 = (int64_t)step_of(0) * TN + col;
+      xn_next = g0 < args.n ? __ldg(args.xnorm + g0) : 0.f;
+    }
     for (int it = 0; it < nit; ++it) {
       const int step = step_of(it);
       const int b = it & 1;
+      const int ss = it % NSTEP;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int64_t grow = (int64_t)step * TN + col;
       const bool valid = grow < args.n;
-      const float xn = valid ? __ldg(args.xnorm + grow) : 0.f;
-      if (w == 0) mbar_wait(bar(B_DFULL + b), bph);
+      const float xn = xn_next;
+      if (it + 1 < nit) {   // prefetch the next step's row norm: a global load must not sit on the step's serial chain
+        const int64_t gn = (int64_t)step_of(it + 1) * TN + col;
+        xn_next = gn < args.n ? __ldg(args.xnorm + gn) : 0.f;
+      }
+      const float thr = fmaf(xn, thrA, thrB);
+      // per-row key offset ||x||^2 + thr: dist' + offset = ||x - c||^2 + thr +- E > 0, so that the float bits of a key
+      // order like unsigned integers, with the key's resolution relative to the true squared distance
+      xoff_s[col] = fmaf(xn, xn, thr);
+      if (threadIdx.x == 0) mbar_expect_tx(bar(B_PX + b), PX_BYTES);   // the peer's partials of this step
+      if (w == 0) {
+        mbar_wait(bar(B_DFULL + b), bph);
+        mbar_wait(bar(B_LEMPTY + b), bph ^ 1u);   // lab[b] of step it - 2 has been consumed by the update role
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       tc_fence_after();
-      const uint32_t src = rank * 4u + (uint32_t)w;
-      const uint32_t poff = (uint32_t)(((b * 8 + (int)src) * TN) * 8);
+      if (w == 0) B2K_TR(it, 5);
 #pragma unroll 1
       for (int g = 0; g < TN / 32; ++g) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_field + (uint32_t)(D_OFF + b * TN + g * 32), v);
+        uint32_t v[2][16];
+        const uint32_t ta = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(D_OFF + b * TN + g * 32);
+        tmem_ld_16x256b_x4(ta, v[0]);
+        tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);
         tmem_wait_ld();
+        uint32_t m1[8], m2[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = pack_key(fmaf(-2.f, __uint_as_float(v[i]), cn), j);
-        uint32_t m1, m2;
-        bfly32(v, lane, m1, m2);
-        const uint32_t o = poff + (uint32_t)((g * 32 + lane) * 8);
-        part_s[(b * 8 + (int)src) * TN + g * 32 + lane] = make_uint2(m1, m2);
-        st_cluster_v2(part_peer0 + o, m1, m2);
+        for (int r = 0; r < 4; ++r) {
+          const float2 xo = *reinterpret_cast<const float2*>(xoff_s + g * 32 + 8 * r + 2 * t0);
+#pragma unroll
+          for (int sx = 0; sx < 2; ++sx) {
+            uint32_t kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // q = 2 h + e: cluster jid0 + 8 q
+              const float dist = fmaf(-2.f, __uint_as_float(v[q >> 1][4 * r + 2 * (q & 1) + sx]), cn4[q]) + (sx ? xo.y : xo.x);
+              kk[q] = (__float_as_uint(dist) & 0xffffff00u) | (jid0 + 8u * (uint32_t)q);
+            }
+            const uint32_t a = min(kk[0], kk[1]), bb = max(kk[0], kk[1]);
+            const uint32_t c = min(kk[2], kk[3]), dd = max(kk[2], kk[3]);
+            m1[2 * r + sx] = min(a, c);
+            m2[2 * r + sx] = min(max(a, c), min(bb, dd));
+          }
+        }
+        bfly2_level<4, 16>(m1, m2, lane);
+        bfly2_level<2, 8>(m1, m2, lane);
+        bfly2_level<1, 4>(m1, m2, lane);
+        const int pi = (b * 8 + (int)src) * TN + g * 32 + cidx;
+        part_s[pi] = make_uint2(m1[0], m2[0]);
+        st_async_v2(part_peer0 + (uint32_t)pi * 8u, m1[0], m2[0], px_peer0 + 8u * (uint32_t)b);
       }
       tc_fence_before();
-      exchange();
+      if (w == 0) B2K_TR(it, 6);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // this CTA's partials
+      mbar_wait(bar(B_PX + b), bph);                    // the peer's partials
+      if (w == 0) B2K_TR(it, 7);
       // combine the 8 partials of my column
       uint32_t M1 = 0xffffffffu, M2 = 0xffffffffu;
 #pragma unroll
@@ -631,9 +738,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
         merge2(M1, M2, p.x, p.y);
       }
       int label = (int)(M1 & 255u);
-      const float M1f = unpack_key(M1), M2f = unpack_key(M2);
-      const float thr = fmaf(xn, thrA, thrB);
-      const bool flag = valid && ((M2f - M1f) < thr);
+      const float M1f = __uint_as_float(M1 & 0xffffff00u);
+      const bool flag = valid && ((__uint_as_float(M2 & 0xffffff00u) - M1f) < thr) &&
+                        !(B2K_PROBE_IS(4) || B2K_PROBE_IS(7) || B2K_PROBE_IS(8));
       candT_s[col] = M1f + thr;
       const uint32_t fl = __ballot_sync(0xffffffffu, flag);
       if (lane == 0) flagw_s[w] = fl;
@@ -641,154 +748,135 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       uint32_t fw[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) fw[i] = flagw_s[i];
-      if ((fw[0] | fw[1] | fw[2] | fw[3]) != 0u) {
-        // ---- exact recheck of the flagged rows (identical decision in both CTAs) ----
-        // (1) candidate masks: clusters whose approximate distance is within thr of the best
+      const int nflag = __popc(fw[0]) + __popc(fw[1]) + __popc(fw[2]) + __popc(fw[3]);
+      if (w == 0) B2K_TR(it, 8);
+      if (nflag != 0) {
+        // ---- exact recheck of the flagged rows (identical flags in both CTAs).  Every cluster whose approximate distance
+        // is within thr of the best is a candidate; each CTA evaluates the candidates among ITS 128 clusters exactly
+        // (fp32 FMA chains over the row in local / distributed shared memory against the fp32 centres, fixed association,
+        // ascending cluster order, strict '<') and the two partial winners are exchanged with one st.async per row. ----
+        if (threadIdx.x == 0) mbar_expect_tx(bar(B_RX), (uint32_t)nflag * 8u);
+        if (flag) {   // compact list of the flagged columns
+          int pos = __popc(fl & ((1u << lane) - 1u));
+#pragma unroll
+          for (int q2 = 0; q2 < 3; ++q2)
+            if (q2 < w) pos += __popc(fw[q2]);
+          flist_s[pos] = (uint8_t)col;
+        }
+        // (1) candidate masks of this CTA's clusters from D (32x32b view: lane = cluster)
 #pragma unroll 1
         for (int wd = 0; wd < 4; ++wd) {
           uint32_t m = fw[wd];
           while (m) {
             const int c = wd * 32 + (__ffs(m) - 1);
             m &= m - 1;
-            const uint32_t dv = tmem_ld_x1(tmem_base + lane_field + (uint32_t)(D_OFF + b * TN + c));
+            const uint32_t dv = tmem_ld_x1(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(D_OFF + b * TN + c));
             tmem_wait_ld();
-            const float dist = fmaf(-2.f, __uint_as_float(dv), cn);
+            const float dist = fmaf(-2.f, __uint_as_float(dv), cn_lane) + xoff_s[c];
             const uint32_t bm = __ballot_sync(0xffffffffu, dist <= candT_s[c]);
-            if (lane == 0) {
-              const uint32_t a = base + OFF_CAND + (uint32_t)((c * 8 + (int)src) * 4);
-              if ((uint32_t)(c >> 6) == rank) cand_s[c * 8 + (int)src] = bm;
-              else st_cluster_u32(mapa_u32(a, peer), bm);
-            }
+            if (lane == 0) cand_s[c * 4 + w] = bm;
           }
         }
         tc_fence_before();
-        exchange();
-        // (2) the row's owner evaluates the candidates exactly, ascending cluster order, strict '<'
-        {
-          const int ss = it % NSTEP;
-          int idx = 0;
-#pragma unroll 1
-          for (int wd = (int)rank * 2; wd < (int)rank * 2 + 2; ++wd) {
-            uint32_t m = fw[wd];
-            while (m) {
-              const int c = wd * 32 + (__ffs(m) - 1);
-              m &= m - 1;
-              if ((idx++ & 3) != w) continue;
-              const int lrow = c & 63;
-              float4 xv[UPL];
-#pragma unroll
-              for (int u2 = 0; u2 < UPL; ++u2) {
-                const int q = lane + 32 * u2;
-                xv[u2] = lds128(ring + (uint32_t)((ss * NCH + (q >> 3)) * SLOT_BYTES + lrow * 128) +
-                                (uint32_t)(((q & 7) ^ (lrow & 7)) << 4));
-              }
-              float best = __int_as_float(0x7f800000);
-              int bj = -1;
-#pragma unroll 1
-              for (int s8 = 0; s8 < 8; ++s8) {
-                uint32_t bm = cand_s[c * 8 + s8];
-                while (bm) {
-                  const int jj = s8 * 32 + (__ffs(bm) - 1);
-                  bm &= bm - 1;
-                  if (jj >= args.k) continue;
-                  float dot = 0.f;
-#pragma unroll
-                  for (int u2 = 0; u2 < UPL; ++u2) {
-                    const int cc = (lane + 32 * u2) * 4;
-                    if (cc < args.d) {
-                      const float4 cv = __ldg(reinterpret_cast<const float4*>(args.C32 + (size_t)jj * args.d + cc));
-                      dot = fmaf(xv[u2].x, cv.x, fmaf(xv[u2].y, cv.y, fmaf(xv[u2].z, cv.z, fmaf(xv[u2].w, cv.w, dot))));
-                    }
-                  }
-#pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-                  const float de = fmaf(-2.f, dot, __ldg(args.cnorm + jj));
-                  if (de < best) { best = de; bj = jj; }
-                  ++n_cand;
-                }
-              }
-              ++n_flag;
-              if (lane == 0) {
-                fin_s[c] = bj;
-                st_cluster_u32(mapa_u32(base + OFF_FIN + (uint32_t)(c * 4), peer), (uint32_t)bj);
-              }
-            }
-          }
-        }
-        exchange();
-        if (flag) {
-          const int f = fin_s[col];
-          if (f >= 0) label = f;
-        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (w == 0) B2K_TR(it, 9);
       }
-      // D (and the exchange buffers of this parity) are drained in this CTA
+      // D of this parity is drained in this CTA
       if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(dempty_leader + 8u * (uint32_t)b)
                      : "memory");
       }
-      // ---- publish: labels (+ sorted row lists in UPD mode) for the update role ----
-      mbar_wait(bar(B_LEMPTY + b), bph ^ 1u);
-      lab_s[b * TN + col] = label;
-      if (valid && (uint32_t)(col >> 6) == rank && args.labels_out != nullptr) args.labels_out[grow] = label;
-      if constexpr (UPD) {
-        uint8_t* cnt = sort_s + SortT::CNT + b * (4 * KH);
-        uint16_t* rows_sorted = reinterpret_cast<uint16_t*>(sort_s + SortT::ROWS) + b * TN;
-        uint8_t* start = sort_s + SortT::START + b * 144;
-        reinterpret_cast<uint32_t*>(cnt + w * KH)[lane] = 0u;
-        __syncwarp();
-        const int kfull = (int)keytab_s[label];
-        const bool mine = valid && (uint32_t)(kfull >> 7) == rank;
-        const int key = mine ? (kfull & 127) : KH;
-        const uint32_t same = __match_any_sync(0xffffffffu, key);
-        const int rnk = __popc(same & ((1u << lane) - 1u));
-        if (mine && rnk == 0) cnt[w * KH + key] = (uint8_t)__popc(same);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        int tot[4];
-        int lane_sum = 0;
+      if (nflag != 0) {
+        // (2) exact evaluation, four rows per warp pass: lane group g = lane >> 3 takes one row, its 8 lanes split the
+        // columns (chunk t, 16-byte unit lane & 7)
+        const int sl = lane & 7;
+#pragma unroll 1
+        for (int i0 = w * 4; i0 < nflag; i0 += 16) {
+          const int i = i0 + (lane >> 3);
+          const bool act = i < nflag;
+          const int c = (int)flist_s[act ? i : 0];
+          const int lrow = c & 63;
+          const bool local = (uint32_t)(c >> 6) == rank;
+          const uint32_t xa0 = ring + (uint32_t)((ss * NCH) * SLOT_BYTES + lrow * 128) + (uint32_t)((sl ^ (lrow & 7)) << 4);
+          const uint32_t xr0 = mapa_u32(xa0, peer);
+          float4 xv[NCH];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = lane * 4 + i;
-          tot[i] = (int)cnt[kk] + (int)cnt[KH + kk] + (int)cnt[2 * KH + kk] + (int)cnt[3 * KH + kk];
-          lane_sum += tot[i];
+          for (int t = 0; t < NCH; ++t) {
+            if (local) xv[t] = lds128(xa0 + (uint32_t)(t * SLOT_BYTES));
+            else xv[t] = ld_cluster_f4(xr0 + (uint32_t)(t * SLOT_BYTES));
+          }
+          float best = __int_as_float(0x7f800000);
+          int bj = -1;
+          int wi = -1;
+          uint32_t bmw = 0;
+          for (;;) {
+            int jj = -1;
+            if (act) {
+              while (bmw == 0u && wi < 3) { ++wi; bmw = cand_s[c * 4 + wi]; }
+              if (bmw != 0u) {
+                jj = (int)rank * KH + wi * 32 + (__ffs(bmw) - 1);
+                bmw &= bmw - 1;
+                if (jj >= args.k) jj = -1;
+              }
+            }
+            if (!__any_sync(0xffffffffu, jj >= 0 || (act && (bmw != 0u || wi < 3)))) break;
+            float dot = 0.f;
+            if (jj >= 0) {
+              const float* pc = args.C32 + (size_t)jj * args.d + sl * 4;
+#pragma unroll
+              for (int t = 0; t < NCH; ++t) {
+                if (t * 32 + sl * 4 < args.d) {
+                  const float4 cv = __ldg(reinterpret_cast<const float4*>(pc + t * 32));
+                  dot = fmaf(xv[t].x, cv.x, fmaf(xv[t].y, cv.y, fmaf(xv[t].z, cv.z, fmaf(xv[t].w, cv.w, dot))));
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (jj >= 0) {
+              const float de = fmaf(-2.f, dot, cnorm_s[jj]);
+              if (de < best) { best = de; bj = jj; }
+              if (sl == 0) ++n_cand;
+            }
+          }
+          if (act && sl == 0) {
+            res_s[c] = make_uint2(__float_as_uint(best), (uint32_t)bj);
+            st_async_v2(resp_peer0 + (uint32_t)c * 8u, __float_as_uint(best), (uint32_t)bj, rx_peer);
+            if (local) ++n_flag;
+          }
         }
-        int incl = lane_sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        int st4[4];
-        st4[0] = incl - lane_sum;
-#pragma unroll
-        for (int i = 1; i < 4; ++i) st4[i] = st4[i - 1] + tot[i - 1];
-        int my_start = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int t = __shfl_sync(0xffffffffu, st4[i], (key < KH ? key : 0) >> 2);
-          if ((key & 3) == i) my_start = t;
-        }
-        int pos = my_start + rnk;
-        if (mine) {
-#pragma unroll
-          for (int q2 = 0; q2 < 3; ++q2)
-            if (q2 < w) pos += (int)cnt[q2 * KH + key];
-          // entry: bit 15 = CTA whose ring holds the row, low bits = byte offset of the row in a chunk slot with the
-          // swizzle phase folded in (address of 16-byte unit u = slot + (entry ^ (u << 4)))
-          const int lrow = col & 63;
-          rows_sorted[pos] = (uint16_t)(((col >> 6) << 15) | (lrow * 128 + ((lrow & 7) << 4)));
-        }
-        if (w == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) start[lane * 4 + i] = (uint8_t)st4[i];
-          if (lane == 31) start[KH] = (uint8_t)incl;
+        if (w == 0) B2K_TR(it, 13);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // this CTA's partial winners
+        mbar_wait(bar(B_RX), rxph);                       // the peer's
+        if (w == 0) B2K_TR(it, 15);
+        rxph ^= 1u;
+        if (flag) {
+          const uint2 mine = res_s[col], theirs = resp_s[col];
+          const uint2 lo = rank == 0 ? mine : theirs, hi = rank == 0 ? theirs : mine;   // lo: clusters 0..127
+          const float vlo = __uint_as_float(lo.x), vhi = __uint_as_float(hi.x);
+          const int jlo = (int)lo.y, jhi = (int)hi.y;
+          int f = jlo;
+          if (jlo < 0 || (jhi >= 0 && vhi < vlo)) f = jhi;
+          if (f >= 0) label = f;
         }
       }
+      // ---- publish the labels: the update warps find their rows themselves (invalid rows: -1) ----
+      lab_s[b * TN + col] = valid ? label : -1;
+      if (valid && (uint32_t)(col >> 6) == rank && args.labels_out != nullptr) args.labels_out[grow] = label;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 0) mbar_arrive(bar(B_LFULL + b));
+      if (w == 0) B2K_TR(it, 10);
     }
-    if (args.rstat != nullptr && lane == 0 && (n_flag | n_cand) != 0ull) {
-      atomicAdd(args.rstat + 0, n_flag);
-      atomicAdd(args.rstat + 1, n_cand);
+    if (args.rstat != nullptr) {   // per-lane counters (counted in the lane-group leaders)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        n_flag += __shfl_xor_sync(0xffffffffu, n_flag, o);
+        n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+      }
+      if (lane == 0 && (n_flag | n_cand) != 0ull) {
+        atomicAdd(args.rstat + 0, n_flag);
+        atomicAdd(args.rstat + 1, n_cand);
+      }
     }
   }
 
@@ -936,6 +1024,16 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   a.labels_out = labels_out;
   a.mind_out = mindist_out;
   a.need_cost = need_cost ? 1 : 0;
+  a.probe = ctx->probe;
+  a.trace = nullptr;
+#if B2K_PROBE
+  if (ctx->profile_fused) {
+    if (!ctx->prof_dev) B2K_CUDA_OK(ctx, cudaMalloc(&ctx->prof_dev, (size_t)1024 * 26 * 8 * sizeof(long long)));
+    B2K_CUDA_OK(ctx, cudaMemsetAsync(ctx->prof_dev, 0, 2 * 26 * 8 * sizeof(long long), s));
+    a.trace = ctx->prof_dev;
+    ctx->prof_grid = 2;
+  }
+#endif
   a.rstat = reinterpret_cast<unsigned long long*>(b + L.off_rstat);
   a.st = st;
 
