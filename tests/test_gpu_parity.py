@@ -39,7 +39,7 @@ def _dev(x):
 def _supported(path, d, k):
     if path == "generic":
         return True
-    return d % 4 == 0 and d <= 128 and k <= 128
+    return d % 4 == 0 and d <= 256 and k <= 256
 
 
 @pytest.mark.parametrize("path", ["generic", "tcgen05"])
@@ -269,10 +269,10 @@ def test_errors_are_loud(ctx):
 
 def test_baseline_config_shapes(ctx):
     """BASELINE.json configs[0] (k=8, n=100k, d=32: full size) and configs[2] (k=256, d=256: a 20k-row slice of the
-    per-GPU partition) against the oracle from an injected init; 'auto' path selection (cfg1 -> tcgen05 kernel,
-    cfg3 -> generic kernels: k, d beyond the fused instantiations)."""
+    per-GPU partition) against the oracle from an injected init; 'auto' path selection: both take a tcgen05 kernel
+    (cfg1 the 3xTF32 one, cfg3 the large-shape 1xTF32 + recheck one, tests/test_gpu_large.py)."""
     ctx.set_option("kernel_path", 0)
-    for (n, d, k, iters, want_path) in [(100_000, 32, 8, 6, 2), (20_000, 256, 256, 3, 1)]:
+    for (n, d, k, iters, want_path) in [(100_000, 32, 8, 6, 2), (20_000, 256, 256, 3, 2)]:
         X, _ = ko.make_blobs(n, d, k, seed=17)
         C0 = X[:k].copy()
         ref = ko.lloyd([X], C0, iters, -1.0)
