@@ -33,12 +33,28 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                    ctypes.c_void_p]
         L.oracle_lloyd.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_threads.restype = None
+        L.oracle_parallel_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+        L.oracle_parallel_copy.restype = None
         _lib = L
     return _lib
 
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(int(n))
+
+
+def first_touch_copy(X: np.ndarray) -> np.ndarray:
+    """A copy of X whose pages are first touched by the OpenMP threads that will read them."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    out = np.empty_like(X)
+    lib().oracle_parallel_copy(out.ctypes.data, X.ctypes.data, X.shape[0], X.shape[1])
+    return out
 
 
 def assign(X: np.ndarray, C: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -31,6 +31,21 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* bench.py's CPU arm: explicit thread count (torchrun exports OMP_NUM_THREADS=1, which must not decide the baseline). */
+void oracle_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
+/* Parallel first touch: copy src into dst with the same static row partitioning the Lloyd loops use, so that on a
+ * multi-socket host every thread's rows live on its own NUMA node. */
+void oracle_parallel_copy(float* dst, const float* src, long long n, int d) {
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < n; ++i) {
+    for (int t = 0; t < d; ++t) dst[i * d + t] = src[i * d + t];
+  }
+}
+
+
 /* labels[i] = argmin_j ||x_i - c_j||^2 (fp64, expanded form), mind[i] = that distance.
  * mind may be NULL. */
 void oracle_assign(const float* X, int64_t n, int d, const float* C, int k,
