@@ -21,6 +21,10 @@ import os
 _TORCHRUN_OMP = os.environ.get("OMP_NUM_THREADS")
 if "LOCAL_RANK" in os.environ and _TORCHRUN_OMP == "1":
     del os.environ["OMP_NUM_THREADS"]
+try:   # before any OpenMP runtime binds the primary thread to its first place
+    _HOST_CORES = len(os.sched_getaffinity(0))
+except Exception:
+    _HOST_CORES = os.cpu_count() or 1
 os.environ.setdefault("OMP_PROC_BIND", "close")
 os.environ.setdefault("OMP_PLACES", "cores")
 
@@ -167,10 +171,7 @@ _CPU_SAMPLE = {}
 
 
 def host_cores() -> int:
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    return _HOST_CORES
 
 
 def cpu_sample(n_rows: int, d: int, k: int, seed: int = 1234):
