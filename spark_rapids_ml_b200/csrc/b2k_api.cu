@@ -100,6 +100,8 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->pair = value ? 1 : 0;
   } else if (k == "variant_t") {
     ctx->force_variant_t = value ? 1 : 0;
+  } else if (k == "tma_box_rows") {
+    ctx->tma_box_rows = (int)value;
   } else if (k == "collect_recheck") {
     ctx->collect_recheck = value ? 1 : 0;
   } else if (k == "profile_fused") {

@@ -98,7 +98,9 @@ struct SortT {
 constexpr int OFF_MISC = (OFF_SORT + SortT::BYTES + 15) & ~15;   // flag words [4] u32, tmem ptr, cost doubles [16]
 constexpr int MISC_FLAGW = 0, MISC_TMEMPTR = 32, MISC_COST = 48;
 constexpr int OFF_BARS = OFF_MISC + 48 + 16 * 8;
-constexpr int B_XFULL = 0;                   // [NSLOT] leader CTA only: both CTAs' TMA boxes of a chunk landed
+constexpr int XG = 4;                        // chunks per x_full barrier: a completed mbarrier wait costs the MMA issuer ~400-500
+                                             // cycles (measured), so it waits per half step (4 chunks), not per chunk
+constexpr int B_XFULL = 0;                   // [NSLOT / XG used] leader CTA only: both CTAs' TMA boxes of a chunk group landed
 constexpr int B_SFREE = B_XFULL + NSLOT;     // [8] step slot may be overwritten (local + remote update roles done)
 constexpr int B_DFULL = B_SFREE + 8;         // [2]
 constexpr int B_DEMPTY = B_DFULL + 2;        // [2] leader CTA only, count 2
@@ -220,37 +222,48 @@ __global__ void __launch_bounds__(256) k_prep_centers_t(const float* __restrict_
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= 256) return;
-  double s = 0.0;
+  double s = 0.0, e = 0.0;
   for (int t = lane; t < DP; t += 32) {
     const float v = (row < k && t < d) ? C[(size_t)row * d + t] : 0.f;
-    Ct[(size_t)row * DP + t] = __uint_as_float(rn_tf32_bits(v));
+    const float r = __uint_as_float(rn_tf32_bits(v));
+    Ct[(size_t)row * DP + t] = r;
     s += (double)v * (double)v;
+    e += ((double)v - (double)r) * ((double)v - (double)r);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) cnorm[row] = row < k ? (float)s : __int_as_float(0x7f800000);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if (lane == 0) {
+    cnorm[row] = row < k ? (float)s : __int_as_float(0x7f800000);
+    cnorm[256 + row] = row < k ? (float)sqrt(e) : 0.f;   // ||c - c~||: the rounding error of this centre's tf32 operand
+  }
 }
 
 // One block of 256 threads: (a) cluster -> update-warp key table balanced by the previous iteration's cluster
 // sizes (32 "virtual" update warps = 16 per CTA of the pair, 8 slots each; key = vwarp * 8 + slot, so that
-// key >> 7 = owning CTA); (b) the recheck threshold thr(x) = thrA * ||x|| + thrB.
+// key >> 7 = owning CTA); (b) the coefficients of the recheck threshold thr(x), see "Bound" below.
 //
-// Bound.  dist'_j = fl(||c_j||^2 - 2 x~.c~_j) with x~ = x truncated (or rounded) to tf32 by the tensor core:
-// |x~_t - x_t| <= 2^-10 |x_t|;  c~ = RN_tf32(c): |c~_t - c_t| <= 2^-11 |c_t|.  Hence
-//   |x~.c~ - x.c| <= (2^-10 + 2^-11 + 2^-21) sum_t |x_t||c_t| <= 1.5005 * 2^-10 ||x|| ||c||       (Cauchy-Schwarz)
+// Bound.  dist'_j = fl(||c_j||^2 - 2 x~.c~_j) with x~ = x cut to tf32 by the tensor core (dx = x~ - x, ||dx|| measured per
+// row by k_row_norms) and c~ = RN_tf32(c) (dc_j = c~_j - c_j, ||dc_j|| measured per centre by k_prep_centers_t):
+//   |x~.c~ - x.c| = |dx.c~ + x.dc| <= ||dx|| ||c~|| + ||x|| ||dc||                                    (Cauchy-Schwarz)
 // tf32 products are exact in fp32; the fp32 accumulation of d <= 256 terms adds at most d * 2^-23 ||x|| ||c||
-// <= 2^-15 ||x|| ||c|| (truncating adder assumed); the final fma rounds once (2^-24 relative) and the key drops 8
-// mantissa bits (2^-15 relative), both relative to |dist'| <= ||c||^2 + 2 ||x|| ||c||.  With Cmax = max_j ||c_j||:
-//   E <= ||x|| Cmax (3.001 * 2^-10 + 2^-14 + 2^-14 + 2^-23) + Cmax^2 (2^-15 + 2^-24)
-// Two approximate distances can be off by E each in opposite directions, so the argmin is proven whenever the gap
-// exceeds 2E <= ||x|| Cmax * 6.26 * 2^-10 + Cmax^2 * 2^-14.  Shipped with a 1.27x margin (also covers the fp32
-// rounding of ||x||, ||c||): thrA = Cmax * 2^-7, thrB = Cmax^2 * 2^-13.
+// <= 2^-15 ||x|| ||c|| (truncating adder assumed); the final fma and add round twice (2^-23 relative) and the key drops
+// 8 mantissa bits (2^-15 relative), relative to the key value ||x - c||^2 + thr <= (||x|| + ||c||)^2 + thr.  With
+// Cmax = max_j ||c_j|| (1 + 2^-11), dCmax = max_j ||dc_j||:
+//   E(x) <= 2 (||dx|| Cmax + ||x|| dCmax) + ||x|| Cmax 2^-14 + (||x|| + Cmax)^2 2^-14
+// Two approximate distances can be off by E each in opposite directions, so the argmin is proven whenever the gap exceeds
+// 2E.  Shipped with a 1.25x margin (also covers the fp32 rounding of the norms themselves):
+//   thr(x) = T0 ||dx|| + T1 ||x|| + T2 ||x||^2 + T3,
+//   T0 = 5 Cmax,  T1 = 5 dCmax + Cmax 2^-12 * 1.25 + Cmax 2^-12 * 1.25,  T2 = 2^-13 * 1.25,  T3 = Cmax^2 2^-13 * 1.25
 __global__ void __launch_bounds__(256) k_tables_t(const double* __restrict__ counts, int k, const float* __restrict__ cnorm,
                                                   uint8_t* __restrict__ keytab, uint8_t* __restrict__ keyinv,
                                                   float* __restrict__ thr, const B2kLoopState* st) {
   if (st != nullptr && st->done) return;
   __shared__ double w[256];
   __shared__ float cmax2[8];
+  __shared__ float dcmax[8];
   const int j = threadIdx.x;
   w[j] = (counts != nullptr && j < k) ? counts[j] : -1.0;   // padding clusters sort last
   float c2 = j < k ? cnorm[j] : 0.f;
@@ -258,11 +271,19 @@ __global__ void __launch_bounds__(256) k_tables_t(const double* __restrict__ cou
   for (int o = 16; o > 0; o >>= 1) c2 = fmaxf(c2, __shfl_xor_sync(0xffffffffu, c2, o));
   if ((j & 31) == 0) cmax2[j >> 5] = c2;
   __syncthreads();
+  float dc = j < k ? cnorm[256 + j] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dc = fmaxf(dc, __shfl_xor_sync(0xffffffffu, dc, o));
+  if ((j & 31) == 0) dcmax[j >> 5] = dc;
+  __syncthreads();
   if (j == 0) {
-    float m = 0.f;
-    for (int i = 0; i < 8; ++i) m = fmaxf(m, cmax2[i]);
-    thr[0] = sqrtf(m) * 0.0078125f;       // Cmax * 2^-7
-    thr[1] = m * 0.0001220703125f;        // Cmax^2 * 2^-13
+    float m = 0.f, dm = 0.f;
+    for (int i = 0; i < 8; ++i) { m = fmaxf(m, cmax2[i]); dm = fmaxf(dm, dcmax[i]); }
+    const float cmax = sqrtf(m) * 1.0005f;
+    thr[0] = 5.f * cmax;
+    thr[1] = 5.f * dm + cmax * 0.0006103515625f;          // 2 * 1.25 * 2^-12
+    thr[2] = 0.000152587890625f;                          // 1.25 * 2^-13
+    thr[3] = cmax * cmax * 0.000152587890625f;
   }
   int key;
   if (counts == nullptr) {
@@ -278,22 +299,32 @@ __global__ void __launch_bounds__(256) k_tables_t(const double* __restrict__ cou
   keyinv[key] = (uint8_t)j;
 }
 
-// xnorm[i] = ||x_i|| (fp32).  One pass over X, once per fit / lloyd / assign call (X is immutable during the call).
-__global__ void __launch_bounds__(256) k_row_norms(const float* __restrict__ X, int64_t n, int d, float* __restrict__ out) {
+// xnorm[i] = { ||x_i||, ||x_i - trunc_tf32(x_i)|| } (fp32).  One pass over X, once per fit / lloyd / assign call (X is
+// immutable during the call).  The second value is the norm of the error the tensor core makes on this row when it cuts
+// the fp32 words to tf32 (an upper bound if the hardware rounds instead: |RN error| <= |truncation error| per element).
+__global__ void __launch_bounds__(256) k_row_norms(const float* __restrict__ X, int64_t n, int d, float2* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d4 = d >> 2;
   for (int64_t row = warp0; row < n; row += nwarps) {
     const float4* p = reinterpret_cast<const float4*>(X + row * d);
-    float s = 0.f;
+    float s = 0.f, e = 0.f;
     for (int t = lane; t < d4; t += 32) {
       const float4 v = __ldcs(p + t);
       s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+      const float ex = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+      const float ey = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+      const float ez = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+      const float ew = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+      e = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, fmaf(ew, ew, e))));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[row] = sqrtf(s);
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    if (lane == 0) out[row] = make_float2(sqrtf(s) * 1.0000002f, sqrtf(e) * 1.0000002f);   // round up
   }
 }
 
@@ -308,8 +339,8 @@ struct TArgs {
   const float* Ct;         // [256][DP] tf32 centres
   const float* C32;        // [k][d] fp32 centres (recheck, min distance)
   const float* cnorm;      // [256]
-  const float* thr;        // [2]
-  const float* xnorm;      // [n]
+  const float* thr;        // [4]
+  const float2* xnorm;     // [n] {||x||, ||x - trunc_tf32(x)||}
   const uint8_t* keytab;   // [256]
   const uint8_t* keyinv;   // [256]
   float* partials;         // [npairs][k*d]
@@ -500,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
         for (int sx = 0; sx < 4; ++sx) {
           uint32_t m = __ballot_sync(0xffffffffu, ((vmask >> sx) & 1u) != 0u &&
                                                        (((keyp >> (8 * sx)) & 255u) - (uint32_t)k0) < (uint32_t)CPW);
-          if (B2K_PROBE_IS(1)) m = 0u;
+          if (B2K_PROBE_IS(1) || B2K_PROBE_IS(9)) m = 0u;
           while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
@@ -595,14 +626,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const int step = step_of(it);
       const int ss = it % NSTEP;
       const uint32_t sph = (uint32_t)(it / NSTEP) & 1u;
-      mbar_wait_cluster_nocall(bar(B_SFREE + ss), sph ^ 1u);   // acquire.cluster: the peer's update role read this slot
+      // CTA-scope wait: a cluster-scope acquire makes ptxas append CCTL.IVALL (L1 invalidate, ~400 cycles) to every wait
+      // (measured: 8 of them per step put 3.6 k cycles on the MMA issuer).  What these barriers order is async-proxy
+      // traffic (TMA writes / UMMA reads) and TMEM (tcgen05 fences), not generic-proxy data in the peer's memory.
+      mbar_wait_nocall(bar(B_SFREE + ss), sph ^ 1u);
       B2K_TR(it, 0);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int slot = ss * NCH + c;
+        const int xb = slot / XG;
         if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(bar(B_XFULL + slot), 2u * SLOT_BYTES);
-          tma_load_2d_pair(ring + slot * SLOT_BYTES, &mapX, xfull_leader0 + 8u * (uint32_t)slot, c * CHUNK,
+          if (rank == 0 && (c % XG) == 0) mbar_expect_tx(bar(B_XFULL + xb), 2u * XG * SLOT_BYTES);
+          tma_load_2d_pair(ring + slot * SLOT_BYTES, &mapX, xfull_leader0 + 8u * (uint32_t)xb, c * CHUNK,
                            step * TN + (int)rank * TNH);
         }
         __syncwarp();
@@ -616,15 +651,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int ss = it % NSTEP;
       const uint32_t sph = (uint32_t)(it / NSTEP) & 1u;
-      mbar_wait_cluster_nocall(bar(B_DEMPTY + b), bph ^ 1u);
+      mbar_wait_nocall(bar(B_DEMPTY + b), bph ^ 1u);
       tc_fence_after();
       B2K_TR(it, 2);
       const uint32_t d_tmem = tmem_base + D_OFF + b * TN;
+#if B2K_PROBE
+      if (B2K_PROBE_IS(12)) {   // all MMAs of the step back to back, no waits (timing only)
+        if (elect_one()) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t bx = ring + (ss * NCH + c) * SLOT_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < CHUNK / 8; ++ks)
+              tc_mma_ts_tf32_pair(d_tmem, tmem_base + (uint32_t)(c * CHUNK + ks * 8), make_kmajor_sw128_desc(bx + ks * 32),
+                                  idesc, (c | ks) != 0 ? 1u : 0u);
+          }
+          tc_commit_pair(bar(B_DFULL + b));
+        }
+        __syncwarp();
+        B2K_TR(it, 4);
+        continue;
+      }
+#endif
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int slot = ss * NCH + c;
-        mbar_wait_cluster_nocall(bar(B_XFULL + slot), sph);
-        tc_fence_after();
+        if ((c % XG) == 0 && !B2K_PROBE_IS(10)) {
+          mbar_wait_nocall(bar(B_XFULL + slot / XG), sph);
+          tc_fence_after();
+        }
         if (c == 0) B2K_TR(it, 3);
         if (c == NCH - 1) B2K_TR(it, 14);
         if (elect_one()) {
@@ -655,7 +710,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     for (int q = 0; q < 4; ++q) cn4[q] = args.cnorm[jid0 + 8 * q];   // q = 2 h + e
     const float cn_lane = args.cnorm[rank * KH + (uint32_t)col];     // 32x32b view (candidate enumeration)
     const int cidx = (lane & 24) | ((lane & 3) << 1) | ((lane >> 2) & 1);   // column of the chunk this lane ends up with
-    const float thrA = args.thr[0], thrB = args.thr[1];
+    const float thr0 = args.thr[0], thr1 = args.thr[1], thr2 = args.thr[2], thr3 = args.thr[3];
     const uint32_t part_peer0 = mapa_u32(base + OFF_PART, peer);
     const uint32_t resp_peer0 = mapa_u32(base + OFF_RESP, peer);
     const uint32_t px_peer0 = mapa_u32(bar(B_PX), peer);
@@ -664,10 +719,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     const uint32_t src = rank * 4u + (uint32_t)w;
     uint32_t rxph = 0;
     unsigned long long n_flag = 0, n_cand = 0;
-    float xn_next = 0.f;
+    float2 xn_next = make_float2(0.f, 0.f);
     if (nit > 0) {
       const int64_t g0 = (int64_t)step_of(0) * TN + col;
-      xn_next = g0 < args.n ? __ldg(args.xnorm + g0) : 0.f;
+      if (g0 < args.n) xn_next = __ldg(args.xnorm + g0);
     }
     for (int it = 0; it < nit; ++it) {
       const int step = step_of(it);
@@ -676,25 +731,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int64_t grow = (int64_t)step * TN + col;
       const bool valid = grow < args.n;
-      const float xn = xn_next;
-      if (it + 1 < nit) {   // prefetch the next step's row norm: a global load must not sit on the step's serial chain
+      const float xn = xn_next.x, dxn = xn_next.y;
+      if (it + 1 < nit) {   // prefetch the next step's row norms: a global load must not sit on the step's serial chain
         const int64_t gn = (int64_t)step_of(it + 1) * TN + col;
-        xn_next = gn < args.n ? __ldg(args.xnorm + gn) : 0.f;
+        xn_next = gn < args.n ? __ldg(args.xnorm + gn) : make_float2(0.f, 0.f);
       }
-      const float thr = fmaf(xn, thrA, thrB);
+      const float thr = fmaf(dxn, thr0, fmaf(xn, fmaf(xn, thr2, thr1), thr3));
       // per-row key offset ||x||^2 + thr: dist' + offset = ||x - c||^2 + thr +- E > 0, so that the float bits of a key
       // order like unsigned integers, with the key's resolution relative to the true squared distance
       xoff_s[col] = fmaf(xn, xn, thr);
-      if (threadIdx.x == 0) mbar_expect_tx(bar(B_PX + b), PX_BYTES);   // the peer's partials of this step
-      if (w == 0) {
-        mbar_wait(bar(B_DFULL + b), bph);
-        mbar_wait(bar(B_LEMPTY + b), bph ^ 1u);   // lab[b] of step it - 2 has been consumed by the update role
-      }
+      if (threadIdx.x == 0 && !B2K_PROBE_IS(9)) mbar_expect_tx(bar(B_PX + b), PX_BYTES);   // the peer's partials of this step
+      // two barriers, two warps: even a completed wait costs several hundred cycles, so they are polled in parallel and
+      // joined by the hardware barrier below
+      if (w == 0) mbar_wait(bar(B_DFULL + b), bph);
+      if (w == 1) mbar_wait(bar(B_LEMPTY + b), bph ^ 1u);   // lab[b] of step it - 2 has been consumed by the update role
       asm volatile("bar.sync 1, 128;" ::: "memory");
       tc_fence_after();
       if (w == 0) B2K_TR(it, 5);
 #pragma unroll 1
-      for (int g = 0; g < TN / 32; ++g) {
+      for (int g = 0; g < (B2K_PROBE_IS(9) ? 0 : TN / 32); ++g) {
         uint32_t v[2][16];
         const uint32_t ta = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(D_OFF + b * TN + g * 32);
         tmem_ld_16x256b_x4(ta, v[0]);
@@ -728,7 +783,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       tc_fence_before();
       if (w == 0) B2K_TR(it, 6);
       asm volatile("bar.sync 1, 128;" ::: "memory");   // this CTA's partials
-      mbar_wait(bar(B_PX + b), bph);                    // the peer's partials
+      if (!B2K_PROBE_IS(9)) mbar_wait(bar(B_PX + b), bph);                    // the peer's partials
       if (w == 0) B2K_TR(it, 7);
       // combine the 8 partials of my column
       uint32_t M1 = 0xffffffffu, M2 = 0xffffffffu;
@@ -738,9 +793,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
         merge2(M1, M2, p.x, p.y);
       }
       int label = (int)(M1 & 255u);
+      if (B2K_PROBE_IS(9)) label = (col * 2 + (int)rank) & 255;
       const float M1f = __uint_as_float(M1 & 0xffffff00u);
       const bool flag = valid && ((__uint_as_float(M2 & 0xffffff00u) - M1f) < thr) &&
-                        !(B2K_PROBE_IS(4) || B2K_PROBE_IS(7) || B2K_PROBE_IS(8));
+                        !(B2K_PROBE_IS(4) || B2K_PROBE_IS(7) || B2K_PROBE_IS(8) || B2K_PROBE_IS(9) || B2K_PROBE_IS(10) || B2K_PROBE_IS(11) || B2K_PROBE_IS(12));
       candT_s[col] = M1f + thr;
       const uint32_t fl = __ballot_sync(0xffffffffu, flag);
       if (lane == 0) flagw_s[w] = fl;
@@ -809,33 +865,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
           int bj = -1;
           int wi = -1;
           uint32_t bmw = 0;
-          for (;;) {
-            int jj = -1;
-            if (act) {
+          auto next_cand = [&]() -> int {   // this CTA's candidates of the row in ascending cluster order, -1 at the end
+            if (!act) return -1;
+            for (;;) {
               while (bmw == 0u && wi < 3) { ++wi; bmw = cand_s[c * 4 + wi]; }
-              if (bmw != 0u) {
-                jj = (int)rank * KH + wi * 32 + (__ffs(bmw) - 1);
-                bmw &= bmw - 1;
-                if (jj >= args.k) jj = -1;
-              }
+              if (bmw == 0u) return -1;
+              const int j = (int)rank * KH + wi * 32 + (__ffs(bmw) - 1);
+              bmw &= bmw - 1;
+              if (j < args.k) return j;
             }
-            if (!__any_sync(0xffffffffu, jj >= 0 || (act && (bmw != 0u || wi < 3)))) break;
-            float dot = 0.f;
-            if (jj >= 0) {
-              const float* pc = args.C32 + (size_t)jj * args.d + sl * 4;
+          };
+          for (;;) {   // two candidates per trip: both centre rows' loads are in flight together
+            const int ja = next_cand();
+            const int jb = ja >= 0 ? next_cand() : -1;
+            if (!__any_sync(0xffffffffu, ja >= 0)) break;
+            float dota = 0.f, dotb = 0.f;
+            if (ja >= 0) {
+              const float* pa = args.C32 + (size_t)ja * args.d + sl * 4;
+              const float* pb = args.C32 + (size_t)(jb >= 0 ? jb : ja) * args.d + sl * 4;
 #pragma unroll
               for (int t = 0; t < NCH; ++t) {
                 if (t * 32 + sl * 4 < args.d) {
-                  const float4 cv = __ldg(reinterpret_cast<const float4*>(pc + t * 32));
-                  dot = fmaf(xv[t].x, cv.x, fmaf(xv[t].y, cv.y, fmaf(xv[t].z, cv.z, fmaf(xv[t].w, cv.w, dot))));
+                  const float4 ca = __ldg(reinterpret_cast<const float4*>(pa + t * 32));
+                  const float4 cb = __ldg(reinterpret_cast<const float4*>(pb + t * 32));
+                  dota = fmaf(xv[t].x, ca.x, fmaf(xv[t].y, ca.y, fmaf(xv[t].z, ca.z, fmaf(xv[t].w, ca.w, dota))));
+                  dotb = fmaf(xv[t].x, cb.x, fmaf(xv[t].y, cb.y, fmaf(xv[t].z, cb.z, fmaf(xv[t].w, cb.w, dotb))));
                 }
               }
             }
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            if (jj >= 0) {
-              const float de = fmaf(-2.f, dot, cnorm_s[jj]);
-              if (de < best) { best = de; bj = jj; }
+            for (int o = 4; o > 0; o >>= 1) {
+              dota += __shfl_xor_sync(0xffffffffu, dota, o);
+              dotb += __shfl_xor_sync(0xffffffffu, dotb, o);
+            }
+            if (ja >= 0) {
+              const float da = fmaf(-2.f, dota, cnorm_s[ja]);
+              if (da < best) { best = da; bj = ja; }
+              if (sl == 0) ++n_cand;
+            }
+            if (jb >= 0) {
+              const float db = fmaf(-2.f, dotb, cnorm_s[jb]);
+              if (db < best) { best = db; bj = jb; }
               if (sl == 0) ++n_cand;
             }
           }
@@ -907,14 +977,14 @@ TLayout t_layout(const B2kFusedPlan& p, int64_t n, int k, int d) {
   TLayout L{};
   size_t o = 0;
   L.off_ct = o; o = al(o + (size_t)256 * p.DP * 4);
-  L.off_cnorm = o; o = al(o + 256 * 4);
+  L.off_cnorm = o; o = al(o + 512 * 4);
   L.off_thr = o; o = al(o + 16);
   L.off_tab = o; o = al(o + 512);
   L.off_rstat = o; o = al(o + 16);
   L.off_partials = o; o = al(o + (size_t)p.P * k * d * 4);
   L.off_counts = o; o = al(o + (size_t)p.P * k * 4);
   L.off_cost = o; o = al(o + (size_t)p.grid * 8);
-  L.off_xnorm = o; o = al(o + (size_t)(n > 0 ? n : 1) * 4);
+  L.off_xnorm = o; o = al(o + (size_t)(n > 0 ? n : 1) * 8);
   L.total = o;
   return L;
 }
@@ -982,7 +1052,7 @@ int b2k_fused_t_prepare(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scrat
   char* b = static_cast<char*>(plan_scratch);
   B2K_CUDA_OK(ctx, cudaMemsetAsync(b + L.off_rstat, 0, 16, s));
   int blocks = ctx->sm_count * 8;
-  k_row_norms<<<blocks, 256, 0, s>>>(X, n, d, reinterpret_cast<float*>(b + L.off_xnorm));
+  k_row_norms<<<blocks, 256, 0, s>>>(X, n, d, reinterpret_cast<float2*>(b + L.off_xnorm));
   ctx->stats.kernel_launches++;
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
@@ -1015,7 +1085,7 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   a.C32 = C;
   a.cnorm = cnorm;
   a.thr = thr;
-  a.xnorm = reinterpret_cast<const float*>(b + L.off_xnorm);
+  a.xnorm = reinterpret_cast<const float2*>(b + L.off_xnorm);
   a.keytab = keytab;
   a.keyinv = keytab + 256;
   a.partials = reinterpret_cast<float*>(b + L.off_partials);

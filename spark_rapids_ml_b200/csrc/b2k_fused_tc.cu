@@ -1180,7 +1180,9 @@ extern "C" int b2k_get_fused_profile(b2k_ctx* ctx, long long* out, int64_t cap, 
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(1024, 1) k_tma_stream(const __grid_constant__ CUtensorMap mapX, int ntiles, int nch,
-                                                      int nslot, int hold, unsigned long long* sink) {
+                                                      int nslot, int hold, unsigned long long* sink, int box_rows) {
+  const int SLOT_BYTES = box_rows * CHUNK * 4;   // shadows the 16 KB constant: option "tma_box_rows" (diagnostic)
+  const int TM = box_rows;
   extern __shared__ uint8_t smem_raw2[];
   const uint32_t base = (smem_u32(smem_raw2) + 1023u) & ~1023u;
   const uint32_t bars = base + (uint32_t)nslot * SLOT_BYTES;
@@ -1238,21 +1240,22 @@ extern "C" int b2k_debug_tma_stream(b2k_ctx* ctx, const float* X, int64_t n, int
                                     float* out_ms) {
   const int spinners = hold_cycles < 0 ? -hold_cycles : 0;   // hold < 0: |hold| extra warps polling an mbarrier
   if (hold_cycles < 0) hold_cycles = 0;
-  if (!ctx || !X || !out_ms || d % CHUNK != 0 || nslot < 1 || nslot > 13)
+  const int box_rows = ctx->tma_box_rows > 0 ? ctx->tma_box_rows : TM;
+  if (!ctx || !X || !out_ms || d % CHUNK != 0 || nslot < 1 || nslot * box_rows > 13 * 128)
     return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_debug_tma_stream: bad argument");
   CUtensorMap mx;
-  B2K_TRY(encode_2d(ctx, &mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)d * 4, CHUNK, TM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-  const int smem = nslot * SLOT_BYTES + 2 * nslot * 8 + 1024 + 128;
+  B2K_TRY(encode_2d(ctx, &mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)d * 4, CHUNK, (uint32_t)box_rows, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  const int smem = nslot * box_rows * CHUNK * 4 + 2 * nslot * 8 + 1024 + 128;
   B2K_CUDA_OK(ctx, cudaFuncSetAttribute(k_tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   B2K_TRY(b2k_scratch_reserve(ctx, 4096));
   cudaEvent_t e0, e1;
   B2K_CUDA_OK(ctx, cudaEventCreate(&e0));
   B2K_CUDA_OK(ctx, cudaEventCreate(&e1));
-  const int ntiles = (int)((n + TM - 1) / TM);
+  const int ntiles = (int)((n + box_rows - 1) / box_rows);
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) B2K_CUDA_OK(ctx, cudaEventRecord(e0, 0));
     k_tma_stream<<<ctx->sm_count, 64 + 32 * spinners, smem, 0>>>(mx, ntiles, d / CHUNK, nslot, hold_cycles,
-                                                 static_cast<unsigned long long*>(ctx->scratch));
+                                                 static_cast<unsigned long long*>(ctx->scratch), box_rows);
   }
   B2K_CUDA_OK(ctx, cudaEventRecord(e1, 0));
   B2K_CUDA_OK(ctx, cudaEventSynchronize(e1));

@@ -16,9 +16,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "first_k":
     C = X[:k].clone()
 ctx = _native.Context(0)
 ctx.set_option("kernel_path", 2)
-ctx.kmeans_lloyd(X, C.clone(), 2, -1.0)
+import os
+if os.environ.get("B2K_PROBE_N"):
+    ctx.set_option("probe", int(os.environ["B2K_PROBE_N"]))
+Cw = C.clone()
+ctx.kmeans_lloyd(X, Cw, 10 if len(sys.argv) > 1 else 2, -1.0)   # settle the centres before tracing a bad start
 ctx.set_option("profile_fused", 1)
-ctx.kmeans_lloyd(X, C.clone(), 1, -1.0)
+ctx.set_option("collect_recheck", 1)
+ctx.kmeans_lloyd(X, Cw, 1, -1.0)
+print("recheck rows / candidates in the traced iteration:", ctx.stats()["recheck_rows"], ctx.stats()["recheck_candidates"], "of", n)
 tr = ctx.fused_profile().reshape(-1)[:256].reshape(2, 8, 16)
 names = {0: "tma:sfree_ok", 1: "upd:keys_ok", 2: "mma:dempty_ok", 3: "mma:xfull0_ok", 14: "mma:xfull7_ok", 4: "mma:issued", 5: "epi:dfull_ok",
          6: "epi:Dloop_done", 7: "epi:exch_done", 8: "epi:flags", 9: "epi:enum_done", 13: "epi:eval_done", 15: "epi:rx_ok", 10: "epi:lfull_sent", 11: "upd:lfull_ok", 12: "upd:rows_done"}
