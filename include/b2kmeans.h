@@ -97,6 +97,9 @@ typedef struct b2k_stats {
   double last_fused_ms;        /* mean device time of the fused kernel over the last lloyd call (CUDA events
                                   on the caller's stream; 0 unless option "time_kernels" is 1) */
   double last_loop_ms;         /* device time of the whole last Lloyd loop (same condition) */
+  double last_reduce_ms;       /* option "time_kernels" = 2: mean device time per iteration of the partial fold, ... */
+  double last_allreduce_ms;    /* ... of the NCCL allreduce of the [k*d+k+1] buffer (0 on one rank), ... */
+  double last_finalize_ms;     /* ... and of finalize */
   int64_t recheck_rows;        /* large-shape kernel (k, d <= 256: 1xTF32 screening): rows of the last lloyd/assign call
                                   whose approximate margin was below the proven error bound and were re-decided
                                   exactly (summed over its passes; 0 unless option "collect_recheck" is 1) */
@@ -108,7 +111,8 @@ const char* b2k_last_error(const b2k_ctx* ctx);
 
 int b2k_ctx_create(int device, b2k_ctx** out);
 int b2k_ctx_destroy(b2k_ctx* ctx);
-/* Options: "kernel_path" (b2k_kernel_path), "time_kernels" (0/1), "check_every" (iterations between host
+/* Options: "kernel_path" (b2k_kernel_path), "time_kernels" (0/1/2: CUDA events around every fused launch; 2 = also
+ * around the partial fold, the allreduce and finalize), "check_every" (iterations between host
  * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "variant_t" (1 = route every shape with k, d <= 256 through the
  * large-shape kernel b2k_fused_t.cu; default 0 = only shapes the 3xTF32 kernel does not cover), "collect_recheck"
  * (1 = lloyd/assign synchronise and fill b2k_stats.recheck_*), "pair" (1 = use the

@@ -71,6 +71,9 @@ class Stats(ctypes.Structure):
         ("last_n_iter", ctypes.c_int32),
         ("last_fused_ms", ctypes.c_double),
         ("last_loop_ms", ctypes.c_double),
+        ("last_reduce_ms", ctypes.c_double),
+        ("last_allreduce_ms", ctypes.c_double),
+        ("last_finalize_ms", ctypes.c_double),
         ("recheck_rows", ctypes.c_int64),
         ("recheck_candidates", ctypes.c_int64),
     ]
@@ -239,6 +242,11 @@ class Context:
             n_b = offsets.shape[0] - 1
         else:
             n_b = int(n_rows) if n_rows is not None else values.size // d
+            # without offsets nothing downstream can see a wrong row width: a batch whose rows are not `d` wide would make
+            # the C side read past the buffer (narrower) or silently re-shape it (wider)
+            if values.size != n_b * d:
+                raise ValueError(f"feature batch holds {values.size} values for {n_b} rows of width {d}: "
+                                 "row width differs from the expected dimension")
         wrote = ctypes.c_int64(0)
         self._check(self._L.b2k_ingest_append(
             self._h, dst.data_ptr(), int(dst.shape[0]), int(d), int(row0), values.ctypes.data,

@@ -288,18 +288,24 @@ class KMeansModel(KMeansClass, _CumlModelWithPredictionCol, _KMeansCumlParams):
             app = DeviceRowAppender(kmeans.ctx, n_cols, first_capacity=n_b)
             if isinstance(df, pd.DataFrame) and alias.data in df.columns:
                 col = df[alias.data]
-                bufs = arrow_list_column_buffers(col)
+                bufs = arrow_list_column_buffers(col, n_cols)
                 if bufs is not None:
                     app.append_values(bufs[0], bufs[1], bufs[2])
                 else:
                     stacked = np.ascontiguousarray(np.array(list(col), order="C"), dtype=np.float32)
+                    if stacked.ndim != 2 or stacked.shape[1] != n_cols:
+                        raise ValueError(f"feature rows do not match the model's {n_cols} columns")
                     app.append_values(stacked.reshape(-1), None, n_b)
             elif isinstance(df, pd.DataFrame):
+                if len(df.columns) != n_cols:
+                    raise ValueError(f"{len(df.columns)} feature columns do not match the model's {n_cols}")
                 cols = [np.ascontiguousarray(df[c].to_numpy()) for c in df.columns]
                 dt = cols[0].dtype
                 app.append_columns([c if c.dtype == dt else c.astype(dt) for c in cols])
             else:
                 arr = np.ascontiguousarray(df, dtype=np.float32)
+                if arr.ndim != 2 or arr.shape[1] != n_cols:
+                    raise ValueError(f"feature rows do not match the model's {n_cols} columns")
                 app.append_values(arr.reshape(-1), None, n_b)
             X = app.finish()
             labels, _ = kmeans.ctx.kmeans_assign(X, kmeans.C)

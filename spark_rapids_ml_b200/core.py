@@ -98,7 +98,7 @@ def _features_from_pdf(pdf: pd.DataFrame, multi_col_names: Optional[List[str]], 
         appender.append_columns(cols)
         return n_b
     col = pdf[alias.data]
-    bufs = arrow_list_column_buffers(col)
+    bufs = arrow_list_column_buffers(col, appender.d)
     if bufs is not None:
         vals, offsets, n_rows = bufs
         appender.append_values(vals, offsets, n_rows)
@@ -106,6 +106,8 @@ def _features_from_pdf(pdf: pd.DataFrame, multi_col_names: Optional[List[str]], 
         stacked = np.array(list(col), order="C")  # reference idiom (core.py:916): slow, kept for compatibility
         if stacked.ndim != 2:
             raise ValueError("feature rows have different lengths")
+        if stacked.shape[1] != appender.d:
+            raise ValueError(f"feature rows are {stacked.shape[1]} wide, expected {appender.d}")
         if stacked.dtype not in (np.float32, np.float64):
             stacked = stacked.astype(np.float32)
         appender.append_values(np.ascontiguousarray(stacked).reshape(-1), None, n_b)

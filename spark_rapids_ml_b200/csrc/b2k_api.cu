@@ -56,7 +56,7 @@ extern "C" int b2k_ctx_create(int device, b2k_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
-  if ((e = cudaHostAlloc((void**)&ctx->h_state, sizeof(B2kLoopState), cudaHostAllocDefault)) != cudaSuccess) {
+  if ((e = cudaHostAlloc((void**)&ctx->h_state, 2 * sizeof(B2kLoopState), cudaHostAllocDefault)) != cudaSuccess) {
     delete ctx;
     return b2k_fail(nullptr, B2K_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
   }
@@ -88,7 +88,7 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
       return b2k_fail(ctx, B2K_ERR_INVALID, "kernel_path must be 0 (auto), 1 (generic) or 2 (tcgen05)");
     ctx->kernel_path = (int)value;
   } else if (k == "time_kernels") {
-    ctx->time_kernels = value ? 1 : 0;
+    ctx->time_kernels = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
   } else if (k == "check_every") {
     if (value < 1) return b2k_fail(ctx, B2K_ERR_INVALID, "check_every must be >= 1");
     ctx->check_every = (int)value;
@@ -250,73 +250,99 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   B2K_CUDA_OK(ctx, cudaMemcpyAsync(B.st, ctx->h_state, sizeof(B2kLoopState), cudaMemcpyHostToDevice, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));  // h_state is reused as the D2H mirror below
 
+  // Events are created BEFORE the timed loop (cudaEventCreate inside it showed up in the multi-GPU per-iteration gap).
+  // time_kernels = 1: around every fused launch; 2: also after the partial reduce, the allreduce and finalize.
+  const int nev_per_it = ctx->time_kernels >= 2 ? 5 : (ctx->time_kernels ? 2 : 0);
   std::vector<cudaEvent_t> ev;
-  cudaEvent_t loop0 = nullptr, loop1 = nullptr;
+  cudaEvent_t loop0 = nullptr, loop1 = nullptr, poll_ev[2] = {nullptr, nullptr};
   if (ctx->time_kernels) {
+    ev.resize((size_t)nev_per_it * (size_t)std::max(max_iter, 0));
+    for (auto& e : ev) B2K_CUDA_OK(ctx, cudaEventCreate(&e));
     B2K_CUDA_OK(ctx, cudaEventCreate(&loop0));
     B2K_CUDA_OK(ctx, cudaEventCreate(&loop1));
-    B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
   }
-
+  B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
+  B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
   if (fused && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, B.plan, B.plan_scratch, X, n, d, k, s));
+  if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
 
-  int launched = 0;
-  bool done = (max_iter == 0);
+  // The host stays one burst ahead of the device: burst b + 1 is enqueued BEFORE the convergence flag of burst b is
+  // read back, so a poll never drains the stream (every hot-loop kernel returns at once when `done` is set, which
+  // makes an over-enqueued burst free).  The read-backs alternate between two pinned mirrors.
+  int launched = 0, slot = 0;
+  bool done = (max_iter == 0), have_pending = false;
+  B2kLoopState* mirror = ctx->h_state;
+  int last_slot = 0;
   while (!done && launched < max_iter) {
     int burst = std::min(ctx->check_every, max_iter - launched);
     for (int b = 0; b < burst; ++b) {
+      cudaEvent_t* e = ctx->time_kernels ? &ev[(size_t)launched * nev_per_it] : nullptr;
       if (fused) {
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (ctx->time_kernels) {
-          B2K_CUDA_OK(ctx, cudaEventCreate(&e0));
-          B2K_CUDA_OK(ctx, cudaEventCreate(&e1));
-          ev.push_back(e0);
-          ev.push_back(e1);
-          B2K_CUDA_OK(ctx, cudaEventRecord(e0, s));
-        }
+        if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[0], s));
         // cluster sizes of the previous iteration (R = [k*d sums | k counts | cost]) drive the update-warp balancing
         B2K_TRY(b2k_launch_fused(ctx, B.plan, B.plan_scratch, X, n, d, C, k, nullptr, nullptr, true, B.st, s,
                                  launched > 0 ? B.R + (size_t)k * d : nullptr));
-        if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(e1, s));
+        if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[1], s));
         float* partials;
         int32_t* counts;
         double* cost_partials;
         b2k_fused_views(B.plan, B.plan_scratch, n, k, d, &partials, &counts, &cost_partials);
         B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.P, B.plan.grid, k, d, B.R, B.st, s));
       } else {
+        if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[0], s));
         B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
         B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, B.cnorm, k, B.labels, nullptr, B.st, s));
         B2K_TRY(b2k_launch_update_generic(ctx, X, n, d, B.labels, k, B.P, B.partials, B.counts, B.st, s));
+        if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[1], s));
         B2K_TRY(b2k_launch_reduce_partials(ctx, B.partials, B.counts, nullptr, B.P, 0, k, d, B.R, B.st, s));
       }
+      if (e && nev_per_it == 5) B2K_CUDA_OK(ctx, cudaEventRecord(e[2], s));
       if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, B.R, rlen, s));
+      if (e && nev_per_it == 5) B2K_CUDA_OK(ctx, cudaEventRecord(e[3], s));
       B2K_TRY(b2k_launch_finalize(ctx, B.R, C, k, d, B.shift_scratch, B.st, s));
+      if (e && nev_per_it == 5) B2K_CUDA_OK(ctx, cudaEventRecord(e[4], s));
       ++launched;
     }
-    B2K_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_state, B.st, sizeof(B2kLoopState), cudaMemcpyDeviceToHost, s));
-    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    done = ctx->h_state->done != 0;
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(&mirror[slot], B.st, sizeof(B2kLoopState), cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaEventRecord(poll_ev[slot], s));
+    if (have_pending) {   // the flag of the PREVIOUS burst, while this one is already queued
+      B2K_CUDA_OK(ctx, cudaEventSynchronize(poll_ev[slot ^ 1]));
+      done = mirror[slot ^ 1].done != 0;
+    }
+    last_slot = slot;
+    have_pending = true;
+    slot ^= 1;
   }
-  if (max_iter == 0) {
-    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
-  }
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  if (have_pending && last_slot != 0) mirror[0] = mirror[last_slot];   // h_state[0] = the final state
+  cudaEventDestroy(poll_ev[0]);
+  cudaEventDestroy(poll_ev[1]);
   if (ctx->time_kernels) {
     B2K_CUDA_OK(ctx, cudaEventRecord(loop1, s));
     B2K_CUDA_OK(ctx, cudaEventSynchronize(loop1));
     float ms = 0.f;
     B2K_CUDA_OK(ctx, cudaEventElapsedTime(&ms, loop0, loop1));
     ctx->stats.last_loop_ms = ms;
-    double acc = 0.0;
+    double acc = 0.0, acc_red = 0.0, acc_comm = 0.0, acc_fin = 0.0;
     int cnt = 0;
-    int iters_done = ctx->h_state->iter;
-    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    const int iters_done = ctx->h_state->iter;
+    for (int i = 0; i < launched && i < iters_done; ++i) {   // launches after convergence are no-ops
       float m = 0.f;
-      cudaEventElapsedTime(&m, ev[i], ev[i + 1]);
-      if ((int)(i / 2) < iters_done) { acc += m; ++cnt; }  // launches after convergence are no-ops
-      cudaEventDestroy(ev[i]);
-      cudaEventDestroy(ev[i + 1]);
+      cudaEvent_t* e = &ev[(size_t)i * nev_per_it];
+      cudaEventElapsedTime(&m, e[0], e[1]);
+      acc += m;
+      if (nev_per_it == 5) {
+        cudaEventElapsedTime(&m, e[1], e[2]); acc_red += m;
+        cudaEventElapsedTime(&m, e[2], e[3]); acc_comm += m;
+        cudaEventElapsedTime(&m, e[3], e[4]); acc_fin += m;
+      }
+      ++cnt;
     }
+    for (auto& e : ev) cudaEventDestroy(e);
     ctx->stats.last_fused_ms = cnt ? acc / cnt : 0.0;
+    ctx->stats.last_reduce_ms = cnt ? acc_red / cnt : 0.0;
+    ctx->stats.last_allreduce_ms = cnt ? acc_comm / cnt : 0.0;
+    ctx->stats.last_finalize_ms = cnt ? acc_fin / cnt : 0.0;
     cudaEventDestroy(loop0);
     cudaEventDestroy(loop1);
   }
@@ -572,17 +598,23 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
   const double ell = oversampling * k;
   const int cap = (int)std::min<int64_t>(rows.total, (int64_t)(4 * ell) + 64);  // per-round candidate cap
   const int Mmax = 1 + rounds * cap + k;
-  // scratch: [0,64K) control | mind[n] | dn[n] | labels[n] | cand[Mmax*d] | newc[cap*d] | hist[Mmax] | assign scratch
+  // scratch (all taken from one arena sized from cap / nranks: no fixed-offset control region):
+  //   idx[cap+8] | n_picked | phi | blocks[1024] | exchange[(cap+1)*(nranks+1)] | mind[n] | dn[n] | labels[n] |
+  //   cand[Mmax*d] | newc[cap*d] | hist[Mmax] | assign scratch
   size_t nn = (size_t)(n > 0 ? n : 1);
-  size_t fixed = 65536 + 3 * align_up(nn * 4, 256) + align_up((size_t)Mmax * d * 4, 256) +
-                 align_up((size_t)cap * d * 4, 256) + align_up((size_t)Mmax * 8, 256) + 4096;
+  const size_t per = (size_t)cap + 1;   // [count | cap indices] per rank in the candidate exchange
+  size_t fixed = align_up((size_t)(cap + 8) * 8, 256) + 256 + 256 + align_up(1024 * 8, 256) +
+                 align_up(per * (size_t)(ctx->nranks + 1) * 8, 256) + 3 * align_up(nn * 4, 256) +
+                 align_up((size_t)Mmax * d * 4, 256) + align_up((size_t)cap * d * 4, 256) +
+                 align_up((size_t)Mmax * 8, 256) + 8192;
   size_t abound = std::max(assign_scratch_bound(ctx, n, d, Mmax, X), assign_scratch_bound(ctx, n, d, cap, X));
   B2K_TRY(b2k_scratch_reserve(ctx, fixed + abound + 4096));
   Arena A(ctx->scratch);
   int64_t* idx_dev = A.take<int64_t>(cap + 8);
   int* n_picked_dev = A.take<int>(8);
   double* phi_dev = A.take<double>(4);
-  A.off = 65536;
+  double* blocks = A.take<double>(1024);
+  int64_t* xchg = A.take<int64_t>(per * (size_t)(ctx->nranks + 1));
   float* mind = A.take<float>(nn);
   float* dn = A.take<float>(nn);
   int32_t* labels = A.take<int32_t>(nn);
@@ -606,7 +638,6 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
     double phi = 0;
     if (r > 0) {
       // phi = sum(mind) (deterministic two-level sum)
-      double* blocks = reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + 32768);
       B2K_TRY(b2k_launch_sum_f32_to_f64(ctx, mind, n, phi_dev, blocks, 1024, s));
     }
     if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, phi_dev, 1, s));
@@ -618,21 +649,16 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
     int np = 0;
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(&np, n_picked_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
     B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    np = std::min(np, cap);
+    np = std::min(np, cap);   // the pick kernel stores at most cap entries; which ones is slot-order dependent, so ...
     if (np > 0) B2K_CUDA_OK(ctx, cudaMemcpy(picked_host.data(), idx_dev, (size_t)np * 8, cudaMemcpyDeviceToHost));
-    std::sort(picked_host.begin(), picked_host.begin() + np);
+    std::sort(picked_host.begin(), picked_host.begin() + np);   // ... the order at least is canonical
     // exchange: every rank learns every rank's picks (global indices), capped in total
     std::vector<int64_t> all;
     if (ctx->nranks == 1) {
       all.assign(picked_host.begin(), picked_host.begin() + np);
     } else {
-      // fixed-size allgather of [count | cap indices] per rank
-      size_t per = (size_t)cap + 1;
-      size_t need = 65536 + 0;  // control region is large enough? use the newc region temporarily
-      (void)need;
-      int64_t* send = reinterpret_cast<int64_t*>(dn);  // dn is free between rounds
-      if ((size_t)nn * 4 < (per * (ctx->nranks + 1)) * 8)
-        return b2k_fail(ctx, B2K_ERR_UNSUPPORTED, "k-means||: partition too small for the candidate exchange");
+      // fixed-size allgather of [count | cap indices] per rank through a dedicated exchange buffer
+      int64_t* send = xchg;
       int64_t* recv = send + per;
       std::vector<int64_t> pack(per, 0);
       pack[0] = np;
@@ -690,11 +716,18 @@ extern "C" int b2k_kmeans_fit(b2k_ctx* ctx, const float* X, int64_t n_local, int
   if (!centers_out) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: centers_out is NULL");
   if (n_init != 1)
     return b2k_fail(ctx, B2K_ERR_UNSUPPORTED, "b2k_kmeans_fit: n_init must be 1 (the reference forces n_init=1)");
-  if (n_local == 0)
-    // reference: core.py:959-962 "A python worker received no data"
-    return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: empty partition (n_local == 0)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B2K_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  {
+    // reference: core.py:959-962 "A python worker received no data".  With a communicator the decision is taken on the
+    // allgathered sizes, so that every rank fails together instead of one rank leaving its peers in a collective.
+    Rows rows;
+    B2K_TRY(gather_sizes(ctx, n_local, &rows, s));
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (rows.sizes[r] == 0)
+        return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: empty partition (rank " + std::to_string(r) +
+                                                  " has n_local == 0)");
+  }
   switch (init_mode) {
     case B2K_INIT_ARRAY:
       if (!init_centers) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: init_centers is NULL");

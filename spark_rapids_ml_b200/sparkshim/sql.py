@@ -271,16 +271,48 @@ class LocalDataFrame:
                     cloudpickle.dump((fn, p, self.arrow_backed_pandas, dict(self.sparkSession.conf_map)), f)
                 procs.append((subprocess.Popen([sys.executable, "-m", "spark_rapids_ml_b200.sparkshim._task",
                                                 str(pid), str(nparts), str(port), pay, res], env=env), res))
+            # Spark fails the whole barrier stage as soon as one task fails: poll all tasks and kill the survivors, which
+            # may be blocked in a collective waiting for the dead peer (reference: core.py:975-981, cuml_context.py:163-167)
+            import time as _time
+
+            deadline = _time.monotonic() + 1800
+            failed = False
+            while True:
+                codes = [pr.poll() for pr, _ in procs]
+                if any(c is not None and c != 0 for c in codes):
+                    failed = True
+                if all(c is not None for c in codes):
+                    break
+                # a task that wrote an error result is as good as dead even if it is still tearing down
+                if not failed:
+                    for _, res in procs:
+                        if os.path.exists(res):
+                            try:
+                                with open(res, "rb") as f:
+                                    if cloudpickle.load(f)[0] != "ok":
+                                        failed = True
+                            except Exception:
+                                pass   # still being written
+                if failed or _time.monotonic() > deadline:
+                    grace = _time.monotonic() + 5.0
+                    while _time.monotonic() < grace and any(pr.poll() is None for pr, _ in procs):
+                        _time.sleep(0.05)
+                    for pr, _ in procs:
+                        if pr.poll() is None:
+                            pr.kill()
+                    for pr, _ in procs:
+                        pr.wait()
+                    break
+                _time.sleep(0.02)
             errors = []
             for pid, (pr, res) in enumerate(procs):
-                try:
-                    pr.wait(timeout=1800)
-                except subprocess.TimeoutExpired:
-                    pr.kill()
-                status, val = "err", f"barrier task {pid} died without a result (exit code {pr.returncode})"
+                status, val = "err", f"barrier task {pid} was killed with the failed stage or died without a result (exit code {pr.returncode})"
                 if os.path.exists(res):
-                    with open(res, "rb") as f:
-                        status, val = cloudpickle.load(f)
+                    try:
+                        with open(res, "rb") as f:
+                            status, val = cloudpickle.load(f)
+                    except Exception:
+                        pass
                 if status == "ok":
                     results.append(val)
                 else:

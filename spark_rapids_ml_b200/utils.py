@@ -71,9 +71,11 @@ class PartitionDescriptor:
 # ------------------------------------------------------------------------------------------------
 # Arrow-buffer access for the ingest fast path
 # ------------------------------------------------------------------------------------------------
-def arrow_list_column_buffers(col: pd.Series) -> Optional[Tuple[np.ndarray, np.ndarray, int]]:
+def arrow_list_column_buffers(col: pd.Series, d: Optional[int] = None) -> Optional[Tuple[np.ndarray, np.ndarray, int]]:
     """If `col` is an Arrow-backed list<T> column, return (flat values ndarray view, int32 offsets, n_rows)
-    WITHOUT copying; else None (object column of ndarrays -> the caller stacks on the host like the reference)."""
+    WITHOUT copying; else None (object column of ndarrays -> the caller stacks on the host like the reference).
+    `d`: the expected row width; a fixed_size_list of another width is an error (list<T> rows are validated against
+    their offsets by the library)."""
     dt = col.dtype
     if not isinstance(dt, pd.ArrowDtype):
         return None
@@ -84,9 +86,11 @@ def arrow_list_column_buffers(col: pd.Series) -> Optional[Tuple[np.ndarray, np.n
     if arr.null_count:
         raise ValueError("null feature rows are not supported")
     if pa.types.is_fixed_size_list(t):
-        d = t.list_size
+        width = t.list_size
+        if d is not None and width != d:
+            raise ValueError(f"feature rows are {width} wide, expected {d}")
         vals = arr.flatten().to_numpy(zero_copy_only=True)
-        return vals, None, len(arr) if d else 0
+        return vals, None, len(arr) if width else 0
     if pa.types.is_list(t):
         offsets = arr.offsets.to_numpy(zero_copy_only=True)
         vals = arr.values.to_numpy(zero_copy_only=True)  # full child buffer; offsets[0] locates the first row
