@@ -607,7 +607,11 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
                  align_up(per * (size_t)(ctx->nranks + 1) * 8, 256) + 3 * align_up(nn * 4, 256) +
                  align_up((size_t)Mmax * d * 4, 256) + align_up((size_t)cap * d * 4, 256) +
                  align_up((size_t)Mmax * 8, 256) + 8192;
-  size_t abound = std::max(assign_scratch_bound(ctx, n, d, Mmax, X), assign_scratch_bound(ctx, n, d, cap, X));
+  // the assign passes below run with 1 .. Mmax centres: small counts take a fused kernel (its scratch holds per-CTA
+  // partial slots and, for the large-shape kernel, the row norms), large ones the generic path
+  size_t abound = 0;
+  for (int kk : {1, std::min(cap, 128), std::min(cap, 256), cap, Mmax})
+    abound = std::max(abound, assign_scratch_bound(ctx, n, d, kk, X));
   B2K_TRY(b2k_scratch_reserve(ctx, fixed + abound + 4096));
   Arena A(ctx->scratch);
   int64_t* idx_dev = A.take<int64_t>(cap + 8);

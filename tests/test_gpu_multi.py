@@ -29,3 +29,65 @@ def test_two_rank_fit_matches_single_rank_and_oracle():
     lab = np.array([r["prediction"] for r in m2.transform(df).collect()])
     cmp = ko.compare_labels(X, C2.astype(np.float32), lab)
     assert cmp["n_mismatch_outside_margin"] == 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_two_rank_fit_large_shape_matches_single_rank():
+    """BASELINE cfg3's (k, d) = (256, 256) over two ranks: the large-shape kernel + the per-iteration allreduce."""
+    from spark_rapids_ml_b200.clustering import KMeans
+    from spark_rapids_ml_b200.sparkshim import LocalSession
+
+    s = LocalSession({"spark.rapids.ml.num_workers.local": "2"})
+    X, _ = ko.make_blobs(30000, 256, 256, seed=6)
+    df = s.from_numpy(X, num_partitions=2)
+    # one iteration from the same (seeded) random rows: only the order of the partial sums differs between 1 and 2 ranks
+    m2 = KMeans(k=256, maxIter=1, tol=1e-6, seed=3, initMode="random", num_workers=2).fit(df)
+    m1 = KMeans(k=256, maxIter=1, tol=1e-6, seed=3, initMode="random", num_workers=1).fit(df)
+    C2, C1 = np.array(m2.cluster_centers_), np.array(m1.cluster_centers_)
+    assert ko.max_center_rel_err(C2, C1) <= 1e-5
+    # several iterations from a random start: blobs that received two initial centres hold rows whose margins are at fp32
+    # noise level, so a last-bit difference of the sums may move a few rows (and their two centres) — nearly all centres
+    # still agree, and the labelling of either model satisfies the parity rule against its own centres
+    m2 = KMeans(k=256, maxIter=5, tol=1e-6, seed=3, initMode="random", num_workers=2).fit(df)
+    m1 = KMeans(k=256, maxIter=5, tol=1e-6, seed=3, initMode="random", num_workers=1).fit(df)
+    C2, C1 = np.array(m2.cluster_centers_), np.array(m1.cluster_centers_)
+    rel = np.linalg.norm(C2 - C1, axis=1) / np.linalg.norm(C1, axis=1)
+    assert (rel <= 1e-4).mean() >= 0.9 and rel.max() <= 0.05
+    lab = np.array([r["prediction"] for r in m2.transform(df).collect()])
+    cmp = ko.compare_labels(X, C2.astype(np.float32), lab)
+    assert cmp["n_mismatch_outside_margin"] == 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_rank_failure_after_comm_init_does_not_hang():
+    """Rank 1 raises inside CumlContext after ncclCommInitRank while rank 0 is already in the fit's first collective:
+    the stage must fail within seconds (rank 1 aborts its communicator, the driver kills the blocked survivor), not
+    hang — reference: cuml_context.py:163-167 (abort on exception), core.py:975-981."""
+    import time
+
+    from spark_rapids_ml_b200.clustering import KMeans
+    from spark_rapids_ml_b200.sparkshim import LocalSession
+
+    s = LocalSession({"spark.rapids.ml.num_workers.local": "2"})
+    X, _ = ko.make_blobs(20000, 64, 16, seed=1)
+    df = s.from_numpy(X, num_partitions=2)
+    est = KMeans(k=16, maxIter=50, tol=0.0, seed=3, initMode="random", num_workers=2)
+    orig = est._get_cuml_fit_func
+
+    def failing(dataset, extra_params=None):
+        fit = orig(dataset, extra_params)
+
+        def wrapped(inputs, params):
+            from spark_rapids_ml_b200.sparkshim import BarrierTaskContext
+
+            if BarrierTaskContext.get().partitionId() == 1:
+                raise RuntimeError("injected failure on rank 1 after comm init")
+            return fit(inputs, params)
+
+        return wrapped
+
+    est._get_cuml_fit_func = failing
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="barrier stage failed"):
+        est.fit(df)
+    assert time.monotonic() - t0 < 120

@@ -48,6 +48,29 @@ def test_barrier_stage_failure_is_loud():
         df.mapInPandas(udf, barrier=True)
 
 
+def test_barrier_stage_failure_kills_blocked_peers_quickly():
+    """A task that fails while its peer is blocked in a rendezvous (the NCCL-collective situation) must fail the whole
+    stage within seconds: the driver kills the survivors instead of waiting out their time-outs
+    (reference behaviour: core.py:975-981, cuml_context.py:163-167)."""
+    import time
+
+    s = LocalSession()
+    df = s.from_numpy(_rows(10, 2), num_partitions=2)
+
+    def udf(it):
+        ctx = BarrierTaskContext.get()
+        list(it)
+        if ctx.partitionId() == 1:
+            raise RuntimeError("rank 1 fails before the rendezvous")
+        ctx.allGather("rank 0 waits for a peer that never arrives")   # blocks (TCPStore time-out: 300 s)
+        yield pd.DataFrame({"ok": [1]})
+
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="barrier stage failed"):
+        df.mapInPandas(udf, barrier=True)
+    assert time.monotonic() - t0 < 60
+
+
 def test_pandas_conversion_modes_and_arrow_fast_path():
     """Arrow-backed columns expose the list child buffer zero-copy; the classic object-column conversion takes the
     stacking path — both must describe the same [n_b, d] values."""
