@@ -318,11 +318,23 @@ def timed_lloyd(torch, dist, ctx, X, C0, steps, dev, world, local_rank, sample_c
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctx.set_option("time_kernels", 1)   # CUDA events around every fused launch of THIS timed loop (roofline)
+    ctx.set_option("time_kernels", 2)   # CUDA events around every fused launch / fold / allreduce / finalize of THIS loop
     ctx.set_option("collect_recheck", 1)
+    if world > 1:
+        # synchronised start: the ranks' hosts leave a collective barrier up to milliseconds apart (OS scheduling), and
+        # that skew would be charged to the first allreduce; all ranks spin to one wall-clock instant (same host)
+        tgt = torch.tensor([time.time() + 0.02], dtype=torch.float64, device=dev)
+        dist.broadcast(tgt, 0)
+        tgt = float(tgt.item())
+        while time.time() < tgt:
+            pass
     e0.record()
+    t_enter = time.time()
     n_iter, shift = ctx.kmeans_lloyd(X, C, steps, -1.0)
+    t_exit = time.time()
     e1.record()
+    if os.environ.get("B2K_DEBUG_TIMING"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] enter {t_enter % 100:.6f} exit {t_exit % 100:.6f}", file=sys.stderr, flush=True)
     torch.cuda.synchronize(dev)
     ctx.set_option("time_kernels", 0)
     ctx.set_option("collect_recheck", 0)
@@ -333,6 +345,16 @@ def timed_lloyd(torch, dist, ctx, X, C0, steps, dev, world, local_rank, sample_c
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item()), ctx.stats(), clocks, shift, C
+
+
+def timed_lloyd_median(torch, dist, ctx, X, C0, steps, dev, world, local_rank, repeats=3):
+    """`repeats` back-to-back timed regions of exactly K steps each (every one bracketed by barrier + synchronize, device
+    timed, max over ranks); the MEDIAN region is reported and all of them are listed.  A single region on a shared host
+    occasionally absorbs a multi-millisecond scheduling hiccup of one rank's process (seen at N=2: 1.19 / 1.63 / 1.19)."""
+    runs = [timed_lloyd(torch, dist, ctx, X, C0, steps, dev, world, local_rank) for _ in range(max(1, repeats))]
+    order = sorted(range(len(runs)), key=lambda i: runs[i][0])
+    mid = order[len(order) // 2]
+    return runs[mid], [r[0] / steps for r in runs]
 
 
 def roofline_record(st, n_local, d, k, kernel, peak, peak_src, tag):
@@ -356,6 +378,8 @@ def roofline_record(st, n_local, d, k, kernel, peak, peak_src, tag):
                        "rule": "the kernel's floor is max(t_hbm, t_tf32): frac = max of the two fractions"},
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "kernel_ms": st["last_fused_ms"], "loop_ms_per_iter": st["last_loop_ms"] / max(1, st["last_n_iter"]),
+            "step_breakdown_ms": {"fused_pass(+centre prep)": st["last_fused_ms"], "partial_fold": st["last_reduce_ms"],
+                                  "allreduce": st["last_allreduce_ms"], "finalize": st["last_finalize_ms"]},
             "algorithmic_bytes_per_launch": alg_bytes, "tensor_flops_per_launch": flops,
             "recheck_rows_per_iter": st["recheck_rows"] / max(1, st["last_n_iter"]),
             "recheck_candidates_per_iter": st["recheck_candidates"] / max(1, st["last_n_iter"])}
@@ -486,7 +510,7 @@ def main():
     X, centers_true = make_blobs_device(torch, dev, n_local, d, k, rank)
     C0, init_mode = pick_init(args.init, args.config, X, centers_true, k, d)
     ctx.kmeans_lloyd(X, C0.clone(), max(args.warmup, 3), -1.0)          # warm-up
-    ms, st, clocks, shift, _ = timed_lloyd(torch, dist, ctx, X, C0, args.steps, dev, world, local_rank)
+    (ms, st, clocks, shift, _), rep_ms = timed_lloyd_median(torch, dist, ctx, X, C0, args.steps, dev, world, local_rank)
     launches = int(st["kernel_launches"])
     path = {1: "generic", 2: "tcgen05"}.get(st["last_path"], "?")
     value = n_total * args.steps / (ms / 1e3)
@@ -608,9 +632,11 @@ def main():
             torch.cuda.synchronize(dev)
             t_init = time.perf_counter() - t_init0
             ctx.kmeans_lloyd(X3, C03.clone(), 3, -1.0)
-            ms3, st3, clocks3, shift3, _ = timed_lloyd(torch, dist, ctx, X3, C03, args.cfg3_steps, dev, world, local_rank)
+            (ms3, st3, clocks3, shift3, _), rep3 = timed_lloyd_median(torch, dist, ctx, X3, C03, args.cfg3_steps, dev, world,
+                                                                      local_rank)
             cfg3 = {"value": n3 * world * args.cfg3_steps / (ms3 / 1e3), "unit": UNIT, "n_gpus": world,
                     "steps": args.cfg3_steps, "warmup": 3, "ms_per_step": ms3 / args.cfg3_steps,
+                    "repeat_ms_per_step": rep3,
                     "config": {"workload": f"cfg3 shape: k={k3}, d={d3}, n={n3}/GPU x {world} GPU, float32 blobs resident in HBM",
                                "k": k3, "d": d3, "n_per_gpu": n3, "kernel_path": {1: "generic", 2: "tcgen05"}.get(st3["last_path"]),
                                "init": mode3, "init_seconds": t_init},
@@ -636,7 +662,9 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "repeat_ms_per_step": rep_ms,
+            "repeats": "3 timed regions of exactly K steps each; the median region is the one reported",
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: KMeans Lloyd iteration, k={k}, n={n_local}/GPU x {world} GPU, d={d}, "
                                    "float32 blobs resident in HBM; fixed 'array' init; tol<0 so every step does full work",

@@ -3,7 +3,10 @@
 // fixed-order partial reduce -> NCCL allreduce of one fused f64 buffer -> finalize, several iterations ahead
 // of the host; convergence lives on the device (B2kLoopState) and is polled every `check_every` iterations.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -207,6 +210,11 @@ struct LoopBuffers {
 static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, float* C, int max_iter, double tol,
                       int* n_iter_out, double* shift_out, cudaStream_t s) {
   if (max_iter < 0) return b2k_fail(ctx, B2K_ERR_INVALID, "lloyd: max_iter < 0");
+  const bool dbg = std::getenv("B2K_DEBUG_TIMING") != nullptr;
+  const auto t_entry = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
   int st_rc;
   const bool fused = want_fused(ctx, n, d, k, X, &st_rc);
   B2K_TRY(st_rc);
@@ -265,6 +273,9 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
   if (fused && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, B.plan, B.plan_scratch, X, n, d, k, s));
   if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
+  const double t_setup = since(t_entry);
+  const auto t_loop = std::chrono::steady_clock::now();
+  double t_first_burst = 0.0;
 
   // The host stays one burst ahead of the device: burst b + 1 is enqueued BEFORE the convergence flag of burst b is
   // read back, so a poll never drains the stream (every hot-loop kernel returns at once when `done` is set, which
@@ -303,6 +314,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
       if (e && nev_per_it == 5) B2K_CUDA_OK(ctx, cudaEventRecord(e[4], s));
       ++launched;
     }
+    if (t_first_burst == 0.0) t_first_burst = since(t_loop);
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(&mirror[slot], B.st, sizeof(B2kLoopState), cudaMemcpyDeviceToHost, s));
     B2K_CUDA_OK(ctx, cudaEventRecord(poll_ev[slot], s));
     if (have_pending) {   // the flag of the PREVIOUS burst, while this one is already queued
@@ -314,6 +326,9 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
     slot ^= 1;
   }
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  if (dbg)
+    fprintf(stderr, "[b2k rank %d] lloyd host timing: setup %.3f ms, first burst enqueued after %.3f ms, loop %.3f ms (%d iterations)\n",
+            ctx->rank, t_setup, t_first_burst, since(t_loop), launched);
   if (have_pending && last_slot != 0) mirror[0] = mirror[last_slot];   // h_state[0] = the final state
   cudaEventDestroy(poll_ev[0]);
   cudaEventDestroy(poll_ev[1]);
