@@ -32,7 +32,8 @@ import pandas as pd
 import pyarrow as pa
 
 from .params import _CumlParams
-from .sparkshim import BarrierTaskContext, LocalDataFrame, Params, Row, get_session
+from .sparkshim import (HAVE_PYSPARK, BarrierTaskContext, EstimatorBase, LocalDataFrame, ModelBase, Params, Row,
+                        get_session)
 from .utils import DeviceRowAppender, arrow_list_column_buffers, get_logger
 
 # same tags as the reference (core.py:128-175) so the worker-side column contract is recognisable
@@ -183,15 +184,27 @@ class _CumlCaller(_CumlParams, _CumlCommon):
             df = df.cast_column(c, want)
         return df, list(input_cols), len(input_cols), "float"
 
-    def _call_cuml_fit_func(self, dataset: LocalDataFrame, partially_collect: bool = True,
-                            paramMaps: Optional[Sequence[Dict[Any, Any]]] = None) -> LocalDataFrame:
+    def _call_cuml_fit_func(self, dataset: Any, partially_collect: bool = True,
+                            paramMaps: Optional[Sequence[Dict[Any, Any]]] = None) -> Any:
+        """Local frames: one barrier task per partition through the shim.  pyspark DataFrames (pyspark importable):
+        the reference's plan — mapInPandas(_train_udf).rdd.barrier().mapPartitions — through spark_binding; returns
+        the collected model rows in that case."""
         self._validate_parameters()
         cls = self.__class__
-        df, multi_col_names, dimension, _ = self._pre_process_data(dataset)
+        spark_df = False
+        if HAVE_PYSPARK:
+            from . import spark_binding
+
+            spark_df = spark_binding.is_spark_dataframe(dataset)
         num_workers = self.num_workers
-        if df.getNumPartitions() != num_workers:
-            df = df.repartition(num_workers)   # core.py:771-772
-        is_local = True
+        if spark_df:
+            df, multi_col_names, dimension, _ = spark_binding.pre_process_data(self, dataset, alias.data)
+            is_local = spark_binding.is_local(dataset)
+        else:
+            df, multi_col_names, dimension, _ = self._pre_process_data(dataset)
+            if df.getNumPartitions() != num_workers:
+                df = df.repartition(num_workers)   # core.py:771-772
+            is_local = True   # the local frame runs on this host: partition id doubles as the GPU id (core.py:377-384)
         params: Dict[str, Any] = {param_alias.cuml_init: dict(self.cuml_params), param_alias.fit_multiple_params: None}
         cuml_fit_func = self._get_cuml_fit_func(dataset, None)
         (enable_nccl, require_ucx) = self._require_nccl_ucx()
@@ -203,7 +216,12 @@ class _CumlCaller(_CumlParams, _CumlCommon):
             from spark_rapids_ml_b200.sparkshim import BarrierTaskContext as _BTC
 
             logger = get_logger(cls)
-            context = _BTC.get()
+            if spark_df:
+                from spark_rapids_ml_b200 import spark_binding as _sb
+
+                context = _sb.current_barrier_context()
+            else:
+                context = _BTC.get()
             partition_id = context.partitionId()
             gpu_id = _CumlCommon._set_gpu_device(context, is_local)
             logger.info("Loading data into device memory (b2k_ingest_append)")
@@ -241,10 +259,12 @@ class _CumlCaller(_CumlParams, _CumlCommon):
             else:
                 yield pd.DataFrame(data=result)
 
+        if spark_df:
+            return spark_binding.run_barrier_fit(df, _train_udf, self._out_schema(), num_workers)
         return df.mapInPandas(_train_udf, schema=self._out_schema(), barrier=True)
 
 
-class _CumlEstimator(_CumlCaller):
+class _CumlEstimator(EstimatorBase, _CumlCaller):
     """reference: core.py:1067-1311."""
 
     def __init__(self) -> None:
@@ -260,7 +280,8 @@ class _CumlEstimator(_CumlCaller):
 
     def _fit_internal(self, dataset: LocalDataFrame, paramMaps: Optional[Sequence[Dict[Any, Any]]]) -> List["_CumlModel"]:
         self.logger.info(f"Training spark-rapids-ml (b200) with {self.num_workers} worker(s) ...")
-        rows = self._call_cuml_fit_func(dataset=dataset, partially_collect=True, paramMaps=paramMaps).collect()
+        res = self._call_cuml_fit_func(dataset=dataset, partially_collect=True, paramMaps=paramMaps)
+        rows = res if isinstance(res, list) else res.collect()   # the pyspark branch returns the collected rows
         self.logger.info("Finished training")
         rows = self._merge_model_chunks(rows, paramMaps)
         models: List["_CumlModel"] = []
@@ -273,9 +294,10 @@ class _CumlEstimator(_CumlCaller):
             models.append(model)
         return models
 
-    def fit(self, dataset: LocalDataFrame, params: Optional[Dict[Any, Any]] = None) -> "_CumlModel":
-        est = self.copy(params) if params else self
-        return est._fit(dataset)
+    if not HAVE_PYSPARK:   # pyspark.ml.Estimator.fit(dataset, params) -> self._fit(dataset) provides this otherwise
+        def fit(self, dataset: LocalDataFrame, params: Optional[Dict[Any, Any]] = None) -> "_CumlModel":
+            est = self.copy(params) if params else self
+            return est._fit(dataset)
 
     def _fit(self, dataset: LocalDataFrame) -> "_CumlModel":
         if self._use_cpu_fallback():
@@ -348,7 +370,7 @@ def _set_params_from_metadata(inst: Any, meta: Dict[str, Any]) -> None:
     inst._float32_inputs = meta["_float32_inputs"]
 
 
-class _CumlModel(_CumlParams, _CumlCommon):
+class _CumlModel(ModelBase, _CumlParams, _CumlCommon):
     """reference: core.py:1356-1753 (KMeans-relevant subset)."""
 
     def __init__(self, *, dtype: Optional[str] = None, n_cols: Optional[int] = None, **model_attributes: Any) -> None:
@@ -391,14 +413,21 @@ class _CumlModel(_CumlParams, _CumlCommon):
         _set_params_from_metadata(inst, meta)
         return inst
 
-    def transform(self, dataset: LocalDataFrame) -> LocalDataFrame:
-        return self._transform(dataset)
+    if not HAVE_PYSPARK:   # pyspark.ml.Transformer.transform(dataset, params) -> self._transform(dataset) otherwise
+        def transform(self, dataset: LocalDataFrame) -> LocalDataFrame:
+            return self._transform(dataset)
 
 
 class _CumlModelWithColumns(_CumlModel):
     """reference: core.py:1797-1941 — keeps the input columns and appends the prediction column."""
 
-    def _transform(self, dataset: LocalDataFrame) -> LocalDataFrame:
+    def _transform(self, dataset: Any) -> Any:
+        if HAVE_PYSPARK:
+            from . import spark_binding
+
+            if spark_binding.is_spark_dataframe(dataset):   # pandas_udf + withColumn (core.py:1846-1878)
+                return spark_binding.transform_with_pandas_udf(
+                    self, dataset, alias.data, lambda ctx, local: _CumlCommon._set_gpu_device(ctx, local, True))
         input_col, input_cols = self._get_input_columns()
         construct, transform_internal, _ = self._get_cuml_transform_func(dataset)
         pred_name = self.getOrDefault("predictionCol")

@@ -1,0 +1,122 @@
+"""The real-pyspark side of the Spark<->worker boundary (SURVEY.md 8b "B1").  Imported only when `import pyspark`
+succeeds; with a LocalDataFrame (this image: no pyspark / JVM) core.py drives the same worker function through the
+shim instead.
+
+What the reference does at these call sites, reproduced here against the public pyspark API:
+  * pre-processing      core.py:463-562   select / cast the feature column(s); VectorUDT -> array via
+                                          pyspark.ml.functions.vector_to_array (:523-525); dimension from first()
+  * barrier fit stage   core.py:1005-1013 dataset.mapInPandas(_train_udf, schema).rdd.barrier().mapPartitions(identity)
+  * local-mode probe    core.py:377-384 / utils._is_local: master URL "local..." -> partition id doubles as the GPU id
+  * transform           core.py:1846-1878 a pandas_udf over struct(*feature columns), appended with withColumn
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Iterator, List, Optional, Tuple
+
+import pandas as pd
+
+
+def is_spark_dataframe(obj: Any) -> bool:
+    try:
+        from pyspark.sql import DataFrame
+    except Exception:
+        return False
+    return isinstance(obj, DataFrame)
+
+
+def is_local(dataset: Any) -> bool:
+    """reference utils._is_local: Spark local mode (one host, partition id == GPU id)."""
+    try:
+        master = dataset.sparkSession.sparkContext.master
+    except Exception:
+        return True
+    return str(master).startswith("local")
+
+
+def pre_process_data(est: Any, dataset: Any, data_alias: str) -> Tuple[Any, Optional[List[str]], int, str]:
+    """-> (selected/cast DataFrame, multi_col_names, dimension, element type) — reference core.py:463-562."""
+    from pyspark.ml.functions import vector_to_array
+    from pyspark.ml.linalg import VectorUDT
+    from pyspark.sql.functions import col
+    from pyspark.sql.types import ArrayType, DoubleType, FloatType
+
+    input_col, input_cols = est._get_input_columns()
+    f32 = bool(est._float32_inputs)
+    if input_col is not None:
+        dtype = dataset.schema[input_col].dataType
+        if isinstance(dtype, VectorUDT):
+            feat = vector_to_array(col(input_col), "float32" if f32 else "float64").alias(data_alias)   # :523-525
+            inner = "float" if f32 else "double"
+        elif isinstance(dtype, ArrayType):
+            elem = dtype.elementType
+            if isinstance(elem, DoubleType) and f32:
+                feat = col(input_col).cast(ArrayType(FloatType())).alias(data_alias)                    # :489-495
+                inner = "float"
+            elif isinstance(elem, (FloatType, DoubleType)):
+                feat = col(input_col).alias(data_alias)
+                inner = "float" if isinstance(elem, FloatType) else "double"
+            else:
+                feat = col(input_col).cast(ArrayType(FloatType() if f32 else DoubleType())).alias(data_alias)
+                inner = "float" if f32 else "double"
+        else:
+            raise ValueError("Unsupported input type.")
+        df = dataset.select(feat)
+        first = df.first()
+        if first is None:
+            raise RuntimeError("A python worker received no data.  Please increase amount of data or use fewer workers.")
+        return df, None, len(first[data_alias]), inner
+    assert input_cols is not None
+    want = FloatType() if f32 else DoubleType()
+    df = dataset.select(*[col(c).cast(want).alias(c) for c in input_cols])                              # :543-557
+    return df, list(input_cols), len(input_cols), "float" if f32 else "double"
+
+
+def run_barrier_fit(df: Any, train_udf: Callable[[Iterator[pd.DataFrame]], Iterator[pd.DataFrame]], out_schema: Any,
+                    num_workers: int) -> List[Any]:
+    """One barrier task per GPU (reference core.py:771-772, 1005-1013); returns the collected model rows."""
+    if df.rdd.getNumPartitions() != num_workers:
+        df = df.repartition(num_workers)
+    pipelined_rdd = df.mapInPandas(train_udf, schema=out_schema).rdd.barrier().mapPartitions(lambda x: x)
+    return pipelined_rdd.collect()
+
+
+def current_barrier_context() -> Any:
+    """Inside a Spark barrier task: pyspark.BarrierTaskContext.get()."""
+    from pyspark import BarrierTaskContext
+
+    return BarrierTaskContext.get()
+
+
+def transform_with_pandas_udf(model: Any, dataset: Any, data_alias: str, set_gpu: Callable[[Any, bool], int]) -> Any:
+    """reference core.py:1797-1941 for a single prediction column: pandas_udf over struct(features) + withColumn."""
+    from pyspark.ml.functions import vector_to_array
+    from pyspark.ml.linalg import VectorUDT
+    from pyspark.sql.functions import col, pandas_udf, struct
+
+    input_col, input_cols = model._get_input_columns()
+    construct, transform_internal, _ = model._get_cuml_transform_func(dataset)
+    local = is_local(dataset)
+    if input_col is not None:
+        dtype = dataset.schema[input_col].dataType
+        if isinstance(dtype, VectorUDT):
+            select_cols = [vector_to_array(col(input_col), "float32" if model._float32_inputs else "float64").alias(data_alias)]
+        else:
+            select_cols = [col(input_col).alias(data_alias)]
+    else:
+        select_cols = [col(c) for c in (input_cols or [])]
+
+    @pandas_udf(model._out_schema(dataset.schema))   # "int"
+    def predict_udf(iterator: Iterator[pd.DataFrame]) -> Iterator[pd.Series]:
+        from pyspark import TaskContext
+
+        gpu = set_gpu(TaskContext.get(), local)
+        device_model = construct(gpu)
+        try:
+            for pdf in iterator:
+                yield transform_internal(device_model, pdf)
+        finally:
+            if hasattr(device_model, "close"):
+                device_model.close()
+
+    pred_name = model.getOrDefault("predictionCol")
+    return dataset.withColumn(pred_name, predict_udf(struct(*select_cols)))
