@@ -17,16 +17,30 @@ from __future__ import annotations
 
 import os
 
-# The CPU arm must not inherit torchrun's OMP_NUM_THREADS=1; thread placement is fixed before any OpenMP runtime loads.
-_TORCHRUN_OMP = os.environ.get("OMP_NUM_THREADS")
-if "LOCAL_RANK" in os.environ and _TORCHRUN_OMP == "1":
-    del os.environ["OMP_NUM_THREADS"]
-try:   # before any OpenMP runtime binds the primary thread to its first place
-    _HOST_CORES = len(os.sched_getaffinity(0))
-except Exception:
-    _HOST_CORES = os.cpu_count() or 1
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def _usable_host_cores():
+    """CPUs this process may actually use: the affinity mask capped by the cgroup CPU quota (this pool's boxes show 128
+    CPUs in the mask with cpu.max = 16 cores: 128 OpenMP threads then run 4x SLOWER than 16 — tools/cpu_arm_probe.py)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    note = f"{n} CPUs in the affinity mask"
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            q = max(1, int(int(quota) / int(period)))
+            if q < n:
+                note = f"cgroup cpu.max = {q} cores of {n} visible CPUs"
+                n = q
+    except Exception:
+        pass
+    return n, note
+
+
+_HOST_CORES, _HOST_CORES_NOTE = _usable_host_cores()   # the CPU arm sets its thread count explicitly (torchrun exports
+                                                        # OMP_NUM_THREADS=1, which stays in force for torch itself)
 
 import argparse
 import json
@@ -146,7 +160,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.01)
 
     def start(self):
         if self.ok:
@@ -260,8 +274,7 @@ def run_reference(args):
                    "k": k, "d": d, "sample_rows": rows},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                          "sample": f"{rows} rows x {args.steps} Lloyd iterations, oracle/kmeans_oracle.c (OpenMP, "
-                                   f"{used} threads set explicitly, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, "
-                                   "parallel first touch, best of 3)"},
+                                   f"{used} threads set explicitly = {_HOST_CORES_NOTE}, parallel first touch, best of 3)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "pyspark.ml.clustering.KMeans (BASELINE configs[0]) cannot run here: no pyspark/JVM in the image; "
                 "the reference's GPU arithmetic (cuML) is absent too, so the CPU arm is the oracle port",
@@ -655,8 +668,8 @@ def main():
         val, dt, used = cpu_oracle_run(rows, d, k, cpu_iters, threads, repeats=3)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                         "sample": f"{rows} rows x {cpu_iters} Lloyd iterations of the same blobs shape (k={k}, d={d}), "
-                                  f"oracle/kmeans_oracle.c OpenMP fp64, {used} threads set explicitly, parallel first touch, "
-                                  f"best of 3: {dt:.2f} s",
+                                  f"oracle/kmeans_oracle.c OpenMP fp64, {used} threads set explicitly = {_HOST_CORES_NOTE}, "
+                                  f"parallel first touch, best of 3: {dt:.2f} s",
                         "other_legs": cpu_sklearn_legs(min(rows, 500_000), d, k, 5)}
 
     if rank == 0:
