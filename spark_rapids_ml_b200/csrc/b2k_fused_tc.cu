@@ -52,7 +52,7 @@ namespace {
 #define B2K_MMA_LANE_POLL 0
 #endif
 #ifndef B2K_MMA_WAIT
-#define B2K_MMA_WAIT mbar_wait_cluster   // alternative: mbar_spin (CTA-scope test_wait loop; same speed, measured)
+#define B2K_MMA_WAIT mbar_wait   // CTA scope: a cluster-scope acquire appends CCTL.IVALL (L1 invalidate) to every wait (r02)
 #endif
 #ifndef B2K_TRACE
 #define B2K_TRACE 0
