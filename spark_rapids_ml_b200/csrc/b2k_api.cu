@@ -97,8 +97,6 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->check_every = (int)value;
   } else if (k == "probe") {
     ctx->probe = (int)value;
-  } else if (k == "pf_dist") {
-    ctx->pf_dist = (int)value;
   } else if (k == "pair") {
     ctx->pair = value ? 1 : 0;
   } else if (k == "variant_t") {

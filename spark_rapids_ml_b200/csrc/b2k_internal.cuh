@@ -39,7 +39,6 @@ struct b2k_ctx {
   int grid_limit = 0;
   int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
   int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
-  int pf_dist = -1;              // option "pf_dist": accepted, ignored (the L2 prefetch experiment was removed)
   int force_variant_t = 0;       // option "variant_t": route every supported shape through b2k_fused_t.cu (tests)
   int tma_box_rows = 0;          // option "tma_box_rows": rows per TMA box of b2k_debug_tma_stream (diagnostic; 0 = 128)
   int collect_recheck = 0;       // option "collect_recheck": fill stats.recheck_* (costs a stream sync per call)

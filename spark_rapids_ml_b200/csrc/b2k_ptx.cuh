@@ -58,10 +58,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
-// warm L2 with a future tile so that the real load (which pins a shared-memory slot) sees L2 latency, not DRAM
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -216,16 +212,6 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
         : "memory");
     if (ok) return;
     if (++spins == (1u << 24)) mbar_timeout(bar, parity);
-  }
-}
-// Lane-parallel poll: every lane with active != 0 waits for ITS OWN barrier/parity; one try_wait instruction carries all
-// the addresses, so the (few hundred cycle) cost of a wait is paid once for the whole set.  Bounded like mbar_wait.
-__device__ __forceinline__ void mbar_wait_lanes(uint32_t my_bar, uint32_t my_parity, bool active) {
-  uint32_t spins = 0;
-  bool ok = !active;
-  while (!__all_sync(0xffffffffu, ok)) {
-    if (!ok) ok = mbar_try_wait(my_bar, my_parity) != 0;
-    if (++spins == (1u << 22)) mbar_timeout(my_bar, my_parity);
   }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
