@@ -41,16 +41,6 @@ namespace {
 #ifndef B2K_PROBE
 #define B2K_PROBE 0
 #endif
-// Round-2 experiment hooks (default off; untested on hardware until enabled with -D...=1 and A/B-measured):
-//   B2K_EPI_PAR_POLL   the second epilogue warp polls lab_empty while the first polls d_full (one join instead of a
-//                      wait by all four warps at the end of the sort)
-//   B2K_MMA_LANE_POLL  the MMA issuer polls the a_full barriers of a chunk pair with two lanes of one try_wait
-#ifndef B2K_EPI_PAR_POLL
-#define B2K_EPI_PAR_POLL 0
-#endif
-#ifndef B2K_MMA_LANE_POLL
-#define B2K_MMA_LANE_POLL 0
-#endif
 #ifndef B2K_MMA_WAIT
 #define B2K_MMA_WAIT mbar_wait   // CTA scope: a cluster-scope acquire appends CCTL.IVALL (L1 invalidate) to every wait (r02)
 #endif
@@ -236,7 +226,6 @@ struct FusedArgs {
   int32_t* labels_out;     // [n] or NULL
   float* mind_out;         // [n] or NULL
   int do_update;
-  int pf_dist;             // unused (the L2 prefetch experiment was removed: +35 % DRAM traffic)
   int probe;               // -DB2K_PROBE=1 builds: timing experiment selector (skips work; wrong results)
   int need_cost;           // compute ||x||^2, min distance and the cost partial (assign / inertia passes)
   const B2kLoopState* st;
@@ -390,16 +379,6 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const uint32_t d_tmem = tmem_base + D_OFF + b * KP;
 #pragma unroll 1
       for (int c = 0; c < G::NCH; ++c) {
-#if B2K_MMA_LANE_POLL
-        // chunk pairs are signalled together (convert CG = 2): lanes 0/1 poll the pair's two a_full barriers at once
-        // when the pair starts; the odd chunk then needs no wait of its own.  (as is even here: NA and NCH are even.)
-        if constexpr (G::NCH % 2 == 0) {
-          if ((c & 1) == 0) {
-            const int my_as = as + (lane & 1);
-            mbar_wait_lanes(bar(G::B_AFULL + my_as), aph, lane < 2);
-          }
-        } else
-#endif
         {
           if constexpr (PAIR) B2K_MMA_WAIT(bar(G::B_AFULL + as), aph);
           else mbar_wait_p(bar(G::B_AFULL + as), aph, prof, pw[1]);
@@ -591,9 +570,6 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
       const int b = ti & 1;
       const uint32_t bph = (uint32_t)(ti >> 1) & 1u;
       if (warp == W_EPI0) mbar_wait_p(bar(G::B_DFULL + b), bph, prof, pw[0]);
-#if B2K_EPI_PAR_POLL
-      if (warp == W_EPI0 + 1) mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);   // joined by bar.sync 5
-#endif
       asm volatile("bar.sync 5, 128;" ::: "memory");
       tc_fence_after();
       B2K_T0(t_e0);
@@ -718,9 +694,7 @@ k_fused_assign_update(const __grid_constant__ CUtensorMap mapX, const __grid_con
         for (int q2 = 0; q2 < 3; ++q2)
           if (q2 < q) pos += (int)cnt[q2 * KP + key];
       }
-#if !B2K_EPI_PAR_POLL
       mbar_wait_p(bar(G::B_LEMPTY + b), bph ^ 1u, prof, pw[2]);
-#endif
       if (valid) rows_sorted[pos] = (uint16_t)(r * 128 + ((r & 7) << 4));
       if (q == 0) {
 #pragma unroll
@@ -1122,7 +1096,6 @@ int b2k_launch_fused(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch,
   a.labels_out = labels_out;
   a.mind_out = mindist_out;
   a.do_update = do_update ? 1 : 0;
-  a.pf_dist = ctx->pf_dist;
   a.probe = ctx->probe;
   a.need_cost = (!do_update || mindist_out != nullptr) ? 1 : 0;
   a.st = st;
