@@ -71,6 +71,7 @@ extern "C" int b2k_ctx_destroy(b2k_ctx* ctx) {
   if (!ctx) return B2K_OK;
   cudaSetDevice(ctx->device);
   if (ctx->nccl) b2k_comm_destroy(ctx);
+  b2k_copy_pool_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->prof_dev) cudaFree(ctx->prof_dev);
   for (int i = 0; i < 2; ++i) {
@@ -101,6 +102,10 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->pair = value ? 1 : 0;
   } else if (k == "variant_t") {
     ctx->force_variant_t = value ? 1 : 0;
+  } else if (k == "ingest_threads") {
+    if (value < 0 || value > 64) return b2k_fail(ctx, B2K_ERR_INVALID, "ingest_threads must be in [0, 64]");
+    b2k_copy_pool_destroy(ctx);
+    ctx->ingest_threads = (int)value;
   } else if (k == "tma_box_rows") {
     ctx->tma_box_rows = (int)value;
   } else if (k == "collect_recheck") {

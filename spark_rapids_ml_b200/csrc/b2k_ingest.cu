@@ -4,11 +4,107 @@
 // buffer goes host -> pinned staging -> HBM once, and a coalesced/vectorised kernel converts (f64/int -> f32)
 // or transposes (d scalar columns -> row-major rows) straight into the reserved [n_max, d] matrix.
 #include <string.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "b2k_internal.cuh"
 
+// The pageable -> pinned staging copy is the bound of the Arrow-batch ingest (one host thread moves ~17-20 GB/s, the PCIe
+// Gen5 link 55 GB/s): a few helper threads split every copy.  Helpers spin for a short while after a job (batches arrive
+// every few hundred microseconds during a partition's ingest) and block on a condition variable when idle.
+struct B2kCopyPool {
+  struct Job { char* dst; const char* src; size_t bytes; };
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<uint64_t> generation{0};
+  std::atomic<int> pending{0};
+  std::atomic<bool> stop{false};
+  Job job{nullptr, nullptr, 0};
+  int nthreads = 1;   // helpers + the caller
+
+  static void slice(const Job& j, int part, int parts, char** d, const char** s, size_t* n) {
+    const size_t per = ((j.bytes / parts) + 4095) & ~(size_t)4095;
+    const size_t lo = std::min(j.bytes, per * (size_t)part);
+    const size_t hi = part == parts - 1 ? j.bytes : std::min(j.bytes, per * (size_t)(part + 1));
+    *d = j.dst + lo; *s = j.src + lo; *n = hi - lo;
+  }
+  void worker(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      // spin briefly for the next job, then sleep
+      auto t0 = std::chrono::steady_clock::now();
+      while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return generation.load(std::memory_order_acquire) != seen || stop.load(); });
+          break;
+        }
+      }
+      if (stop.load()) return;
+      seen = generation.load(std::memory_order_acquire);
+      char* d; const char* s; size_t n;
+      slice(job, id, nthreads, &d, &s, &n);
+      if (n) memcpy(d, s, n);
+      pending.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+  explicit B2kCopyPool(int n) : nthreads(n) {
+    for (int i = 1; i < n; ++i) workers.emplace_back([this, i] { worker(i); });
+  }
+  ~B2kCopyPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop.store(true); }
+    cv.notify_all();
+    for (auto& t : workers) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (nthreads <= 1 || bytes < ((size_t)512 << 10)) { memcpy(dst, src, bytes); return; }
+    job = Job{static_cast<char*>(dst), static_cast<const char*>(src), bytes};
+    pending.store(nthreads - 1, std::memory_order_release);
+    { std::lock_guard<std::mutex> lk(mu); generation.fetch_add(1, std::memory_order_acq_rel); }
+    cv.notify_all();
+    char* d; const char* s; size_t n;
+    slice(job, 0, nthreads, &d, &s, &n);
+    if (n) memcpy(d, s, n);
+    while (pending.load(std::memory_order_acquire) != 0) { /* helpers finish within microseconds of the caller */ }
+  }
+};
+
+void b2k_copy_pool_destroy(b2k_ctx* ctx) {
+  delete static_cast<B2kCopyPool*>(ctx->copy_pool);
+  ctx->copy_pool = nullptr;
+}
+
 namespace {
 constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+
+B2kCopyPool* copy_pool(b2k_ctx* ctx) {
+  if (!ctx->copy_pool) {
+    int n = ctx->ingest_threads;
+    if (n <= 0) {   // default: 4, capped by the CPUs this process may use (affinity, cgroup quota)
+      long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+      FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+      if (f) {
+        char q[64] = {0};
+        long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+          long quota = atol(q) / period;
+          if (quota >= 1 && quota < cpus) cpus = quota;
+        }
+        fclose(f);
+      }
+      n = (int)std::max(1L, std::min(4L, cpus / 2));
+    }
+    ctx->copy_pool = new B2kCopyPool(n);
+  }
+  return static_cast<B2kCopyPool*>(ctx->copy_pool);
+}
 
 __host__ __device__ inline size_t dtype_size(int t) {
   switch (t) {
@@ -181,7 +277,7 @@ extern "C" int b2k_ingest_append(b2k_ctx* ctx, float* dst, int64_t n_max, int d,
         B2K_CUDA_OK(ctx, cudaEventSynchronize(ctx->stage_evt[b]));  // previous use of this slot has drained
         const void* hsrc = src + done * es;
         if (!pinned_src) {
-          memcpy(ctx->pinned[b], hsrc, cnt * es);
+          copy_pool(ctx)->copy(ctx->pinned[b], hsrc, cnt * es);
           hsrc = ctx->pinned[b];
         }
         if (src_dtype == B2K_F32) {

@@ -60,6 +60,8 @@ struct b2k_ctx {
   size_t dev_stage_bytes = 0;
   cudaEvent_t stage_evt[2] = {nullptr, nullptr};
   int stage_next = 0;
+  void* copy_pool = nullptr;     // B2kCopyPool (b2k_ingest.cu): helper threads of the pageable -> pinned staging copy
+  int ingest_threads = 0;        // option "ingest_threads": threads of that copy (0 = default 4, capped by the CPU quota)
   // pinned host mirror of the loop state (convergence polls)
   B2kLoopState* h_state = nullptr;
   // TMA descriptor encoder (driver entry point, resolved lazily)
@@ -86,6 +88,7 @@ int b2k_fail(b2k_ctx* ctx, int code, const std::string& msg);
   } while (0)
 
 int b2k_scratch_reserve(b2k_ctx* ctx, size_t bytes);
+void b2k_copy_pool_destroy(b2k_ctx* ctx);
 
 // ------------------------------------------------------------------------------------------------
 // generic (any k, d) kernels — b2k_generic.cu
