@@ -530,16 +530,14 @@ std::vector<int64_t> sample_distinct(std::mt19937_64& rng, int64_t total, int m)
   return chosen;
 }
 
-// Weighted greedy k-means++ followed by a few weighted Lloyd steps on the (small) candidate set — host side.
-void reduce_candidates(const std::vector<float>& P, const std::vector<double>& wts, int M, int d, int k,
-                       std::mt19937_64& rng, std::vector<float>* out) {
-  std::vector<double> C((size_t)k * d), d2(M), nd2(M), bestd2(M);
-  auto sq = [&](int a, const double* c) {
-    double s = 0;
-    const float* p = &P[(size_t)a * d];
-    for (int t = 0; t < d; ++t) { double df = (double)p[t] - c[t]; s += df * df; }
-    return s;
-  };
+// Weighted greedy k-means++ followed by a few weighted Lloyd steps on the (small) candidate set — host side, on the
+// candidate-to-candidate squared distances D2 [M x M] computed on the device (every k-means++ centre IS a candidate, so
+// the greedy phase is table look-ups: k * trials * M instead of k * trials * M * d operations).
+void reduce_candidates(const std::vector<float>& P, const std::vector<float>& D2, const std::vector<double>& wts, int M, int d,
+                       int k, std::mt19937_64& rng, std::vector<float>* out) {
+  std::vector<double> d2(M), nd2(M), bestd2(M);
+  std::vector<int> chosen;
+  chosen.reserve(k);
   auto pick = [&](const std::vector<double>& prob, double tot) {
     std::uniform_real_distribution<double> U(0.0, tot);
     double u = U(rng), acc = 0;
@@ -550,10 +548,9 @@ void reduce_candidates(const std::vector<float>& P, const std::vector<double>& w
   double tot = 0;
   for (int i = 0; i < M; ++i) { prob[i] = wts[i]; tot += prob[i]; }
   int first = pick(prob, tot);
-  for (int t = 0; t < d; ++t) C[t] = P[(size_t)first * d + t];
-  for (int i = 0; i < M; ++i) d2[i] = sq(i, &C[0]);
+  chosen.push_back(first);
+  for (int i = 0; i < M; ++i) d2[i] = (double)D2[(size_t)i * M + first];
   const int trials = 2 + (int)std::log((double)std::max(k, 2));
-  std::vector<double> cand(d);
   for (int j = 1; j < k; ++j) {
     tot = 0;
     for (int i = 0; i < M; ++i) { prob[i] = wts[i] * d2[i]; tot += prob[i]; }
@@ -561,33 +558,49 @@ void reduce_candidates(const std::vector<float>& P, const std::vector<double>& w
     int best_c = 0;
     for (int tr = 0; tr < trials; ++tr) {
       int c = tot > 0 ? pick(prob, tot) : (int)(rng() % M);
-      for (int t = 0; t < d; ++t) cand[t] = P[(size_t)c * d + t];
       double pot = 0;
-      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], sq(i, cand.data())); pot += wts[i] * nd2[i]; }
+      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], (double)D2[(size_t)i * M + c]); pot += wts[i] * nd2[i]; }
       if (best_pot < 0 || pot < best_pot) { best_pot = pot; best_c = c; bestd2 = nd2; }
     }
-    for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = P[(size_t)best_c * d + t];
+    chosen.push_back(best_c);
     d2 = bestd2;
   }
+  // weighted Lloyd refinement on the candidates (fp32 dot products, fp64 sums)
+  std::vector<float> C((size_t)k * d), cn(k);
+  for (int j = 0; j < k; ++j)
+    for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = P[(size_t)chosen[j] * d + t];
   std::vector<int> lab(M);
+  std::vector<double> S((size_t)k * d), W(k);
   for (int it = 0; it < 10; ++it) {
+    for (int j = 0; j < k; ++j) {
+      float s2 = 0.f;
+      for (int t = 0; t < d; ++t) s2 += C[(size_t)j * d + t] * C[(size_t)j * d + t];
+      cn[j] = s2;
+    }
     for (int i = 0; i < M; ++i) {
-      double b = 1e300;
+      const float* p = &P[(size_t)i * d];
+      float b = 3.4e38f;
       int bj = 0;
-      for (int j = 0; j < k; ++j) { double s = sq(i, &C[(size_t)j * d]); if (s < b) { b = s; bj = j; } }
+      for (int j = 0; j < k; ++j) {
+        const float* c = &C[(size_t)j * d];
+        float dot = 0.f;
+        for (int t = 0; t < d; ++t) dot += p[t] * c[t];
+        const float dist = cn[j] - 2.f * dot;
+        if (dist < b) { b = dist; bj = j; }
+      }
       lab[i] = bj;
     }
-    std::vector<double> S((size_t)k * d, 0.0), W(k, 0.0);
+    std::fill(S.begin(), S.end(), 0.0);
+    std::fill(W.begin(), W.end(), 0.0);
     for (int i = 0; i < M; ++i) {
       W[lab[i]] += wts[i];
       for (int t = 0; t < d; ++t) S[(size_t)lab[i] * d + t] += wts[i] * (double)P[(size_t)i * d + t];
     }
     for (int j = 0; j < k; ++j)
       if (W[j] > 0)
-        for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = S[(size_t)j * d + t] / W[j];
+        for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = (float)(S[(size_t)j * d + t] / W[j]);
   }
-  out->resize((size_t)k * d);
-  for (size_t e = 0; e < (size_t)k * d; ++e) (*out)[e] = (float)C[e];
+  *out = C;
 }
 }  // namespace
 
@@ -720,8 +733,20 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
   B2K_CUDA_OK(ctx, cudaMemcpyAsync(wts.data(), hist, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
   for (auto& w : wts) w = std::max(w, 1e-12);
+  // candidate-to-candidate squared distances on the device (identical on every rank: same candidates, same kernel)
+  std::vector<float> D2h((size_t)M * M);
+  {
+    B2K_TRY(b2k_scratch_reserve(ctx, fixed + abound + 4096 + (size_t)M * M * 4 + 1024));
+    // the scratch may have moved: only `cand` is needed from here on, and it was copied to P above
+    float* candd = reinterpret_cast<float*>(static_cast<char*>(ctx->scratch));
+    float* D2d = candd + (size_t)M * d;
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(candd, P.data(), P.size() * 4, cudaMemcpyHostToDevice, s));
+    B2K_TRY(b2k_launch_pairwise_sqdist(ctx, candd, M, d, D2d, s));
+    B2K_CUDA_OK(ctx, cudaMemcpyAsync(D2h.data(), D2d, D2h.size() * 4, cudaMemcpyDeviceToHost, s));
+    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  }
   std::vector<float> Ck;
-  reduce_candidates(P, wts, M, d, k, rng, &Ck);  // same seed + same inputs => identical on every rank
+  reduce_candidates(P, D2h, wts, M, d, k, rng, &Ck);  // same seed + same inputs => identical on every rank
   B2K_CUDA_OK(ctx, cudaMemcpyAsync(C, Ck.data(), Ck.size() * 4, cudaMemcpyHostToDevice, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
   return B2K_OK;

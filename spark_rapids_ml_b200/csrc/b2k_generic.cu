@@ -529,3 +529,40 @@ int b2k_launch_histogram(b2k_ctx* ctx, const int32_t* labels, int64_t n, int m, 
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// D2[i][j] = ||p_i - p_j||^2 for the (few thousand) k-means|| candidates: feeds the weighted greedy k-means++ of the
+// candidate reduction, which would otherwise recompute M*d-long distances k*trials times on one host thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pairwise_sqdist(const float* __restrict__ P, int M, int d, float* __restrict__ D2) {
+  __shared__ float a[16][33], b[16][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int t0 = 0; t0 < d; t0 += 32) {
+    for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const int gi = blockIdx.y * 16 + r, gj = blockIdx.x * 16 + r;
+      a[r][c] = (gi < M && t0 + c < d) ? P[(size_t)gi * d + t0 + c] : 0.f;
+      b[r][c] = (gj < M && t0 + c < d) ? P[(size_t)gj * d + t0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float df = a[ty][c] - b[tx][c];
+      acc += (double)df * (double)df;
+    }
+    __syncthreads();
+  }
+  if (i < M && j < M) D2[(size_t)i * M + j] = (float)acc;
+}
+
+int b2k_launch_pairwise_sqdist(b2k_ctx* ctx, const float* P, int M, int d, float* D2, cudaStream_t s) {
+  dim3 grid((M + 15) / 16, (M + 15) / 16);
+  k_pairwise_sqdist<<<grid, 256, 0, s>>>(P, M, d, D2);
+  ctx->stats.kernel_launches++;
+  ctx->stats.generic_launches++;
+  B2K_CUDA_OK(ctx, cudaGetLastError());
+  return B2K_OK;
+}

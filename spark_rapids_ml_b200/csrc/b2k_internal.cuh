@@ -125,6 +125,7 @@ int b2k_launch_bernoulli_pick(b2k_ctx* ctx, const float* mind, int64_t n, int64_
                               int* n_picked, int cap, cudaStream_t s);
 int b2k_launch_histogram(b2k_ctx* ctx, const int32_t* labels, int64_t n, int m, double* hist,
                          cudaStream_t s);
+int b2k_launch_pairwise_sqdist(b2k_ctx* ctx, const float* P, int M, int d, float* D2, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 fused kernel — b2k_fused_tc.cu

@@ -226,6 +226,23 @@ def test_init_modes_statistical(ctx):
     np.testing.assert_array_equal(a["cluster_centers_"].cpu().numpy(), b["cluster_centers_"].cpu().numpy())
 
 
+def test_kmeans_parallel_init_large_k(ctx):
+    """k-means|| with k >= 1024 (its scratch comes from one arena sized from the candidate cap: a fixed 64 KB control
+    region used to overlap the min-distance array from k ~ 1008 on): the seeding must find (nearly) every blob."""
+    import torch
+
+    ctx.set_option("kernel_path", 0)
+    n, d, k = 200_000, 32, 1024
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ctr = torch.rand((k, d), generator=g, device="cuda") * 20 - 10
+    X = (ctr[torch.randint(0, k, (n,), generator=g, device="cuda")] + 0.2 * torch.randn((n, d), generator=g, device="cuda")).contiguous()
+    a = ctx.kmeans_fit(X, k, init="scalable-k-means++", max_iter=5, tol=1e-6, seed=1)
+    b = ctx.kmeans_fit(X, k, init="scalable-k-means++", max_iter=5, tol=1e-6, seed=1)
+    ideal = n * d * 0.04                     # sigma^2 * d per row if every blob has its own centre
+    assert a["inertia_"] <= 6.0 * ideal, (a["inertia_"], ideal)   # a random start leaves ~1/e of the blobs without a centre: >> this
+    np.testing.assert_array_equal(a["cluster_centers_"].cpu().numpy(), b["cluster_centers_"].cpu().numpy())   # seeded: reproducible
+
+
 def test_ingest_layouts(ctx):
     import torch
 
