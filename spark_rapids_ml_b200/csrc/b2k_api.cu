@@ -301,7 +301,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
         int32_t* counts;
         double* cost_partials;
         b2k_fused_views(B.plan, B.plan_scratch, n, k, d, &partials, &counts, &cost_partials);
-        B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.P, B.plan.grid, k, d, B.R, B.st, s));
+        B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.P, B.plan.Pc, k, d, B.R, B.st, s));
       } else {
         if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[0], s));
         B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
@@ -412,7 +412,7 @@ static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const flo
       double* cost_partials;
       b2k_fused_views(plan, ps, n, k, d, &partials, &counts, &cost_partials);
       // fold the per-CTA cost partials in index order
-      B2K_TRY(b2k_launch_fold_f64(ctx, cost_partials, plan.grid, cost_dev, s));
+      B2K_TRY(b2k_launch_fold_f64(ctx, cost_partials, plan.Pc, cost_dev, s));
     }
     if (ctx->collect_recheck) {
       unsigned long long rs[2];

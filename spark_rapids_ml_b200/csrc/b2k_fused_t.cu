@@ -13,10 +13,12 @@
 //     into one ordered 32-bit key, and a shuffle butterfly finds the smallest AND second smallest key of every row
 //     across the 32 lanes of a warp; 4 warps x 2 CTAs exchange their partials through (distributed) shared memory.
 //     A row whose gap is below the PROVEN bound thr = 2E (E: worst-case error of one dist', see k_tables_t) is
-//     re-decided exactly: every cluster within thr of the best is a candidate, the row's owner evaluates the
-//     candidates in fp32 (FMA chains over the row in shared memory against the fp32 centres, fixed-order tree) with
-//     strict '<' in ascending cluster order (= lowest index on ties).  Rows outside the bound provably have the
-//     same argmin in exact arithmetic, so labels match the 3xTF32 / fp32 path.
+//     DEFERRED: the epilogue appends it (row id + the bit mask of every cluster within thr of the best = its
+//     candidates) to the CTA pair's segment of a fix-up list and publishes no label for it, so the pass never
+//     waits for an exact evaluation.  k_fix_labels_t then decides those rows exactly (fp32 dot products against the
+//     fp32 centres, ascending cluster order, strict '<' = lowest index on ties) and k_fix_accum_t adds them to one
+//     extra partial-sum slot (fixed list order: deterministic).  Rows outside the bound provably have the same
+//     argmin in exact arithmetic, so labels match the 3xTF32 / fp32 path.
 //   * update: per-cluster sums live in REGISTERS, one [256, 256] accumulator set per CTA PAIR (each CTA: 128
 //     clusters x 256 columns = 64 registers per update thread).  Rows are counting-sorted by (owner warp, cluster,
 //     row) as in b2k_fused_tc.cu; a warp reads its rows from the local ring or, for the peer's rows, through
@@ -26,7 +28,7 @@
 //
 // Replaces (for these shapes) cuML's fusedL2NN + reduce_rows_by_key reached from
 // spark_rapids_ml/clustering.py:412-415.  Algorithmic HBM bytes per launch: 4*n*d (X once)
-// + 4*n (row norms) [+ 4*n labels / 4*n mindist when requested] + 74 * (k*d + k) * 4 partials.
+// + 8*n (row norms) [+ 4*n labels / 4*n mindist when requested] + 75 * (k*d + k) * 4 partials + 40 B per deferred row.
 #include <float.h>
 #include <stdio.h>
 
@@ -82,14 +84,8 @@ constexpr int NTHREADS = NWARPS * 32;
 constexpr int OFF_RING = 0;
 constexpr int OFF_PART = NSLOT * SLOT_BYTES;            // uint2 part[2][8 sources][128 columns]: (best, second) keys
 constexpr int OFF_LAB = OFF_PART + 2 * 8 * TN * 8;      // int32 lab[2][128]: final labels of the step
-constexpr int OFF_CAND = OFF_LAB + 2 * TN * 4;          // u32 cand[128][4]: candidate bit masks (this CTA's clusters)
-constexpr int OFF_CANDT = OFF_CAND + TN * 4 * 4;        // f32 candT[128]: best + thr per column
-constexpr int OFF_RES = OFF_CANDT + TN * 4;             // uint2 res[128]: this CTA's exact partial winner (value, cluster)
-constexpr int OFF_RESP = OFF_RES + TN * 8;              // uint2 resp[128]: the peer's (st.async)
-constexpr int OFF_XOFF = OFF_RESP + TN * 8;             // f32 xoff[128]: per-row key offset ||x||^2 + thr
-constexpr int OFF_FLIST = OFF_XOFF + TN * 4;            // u8 flist[128]: flagged columns of the step
-constexpr int OFF_CNORM = OFF_FLIST + TN;               // f32 cnorm[256]: ||c||^2 of every centre (exact recheck)
-constexpr int OFF_SORT = OFF_CNORM + 256 * 4;           // cluster <-> update-warp key tables, see SortT
+constexpr int OFF_XOFF = OFF_LAB + 2 * TN * 4;          // f32 xoff[128]: per-row key offset ||x||^2 + thr
+constexpr int OFF_SORT = OFF_XOFF + TN * 4;             // cluster <-> update-warp key tables, see SortT
 struct SortT {
   static constexpr int KEYTAB = 0;                      // u8 [256] cluster -> key (cta*128 + warp*8 + slot)
   static constexpr int KEYINV = KEYTAB + 256;           // u8 [256] key -> cluster
@@ -104,8 +100,7 @@ constexpr int B_XFULL = 0;                   // [NSLOT / XG used] leader CTA onl
 constexpr int B_SFREE = B_XFULL + NSLOT;     // [8] step slot may be overwritten (local + remote update roles done)
 constexpr int B_DFULL = B_SFREE + 8;         // [2]
 constexpr int B_DEMPTY = B_DFULL + 2;        // [2] leader CTA only, count 2
-constexpr int B_RX = B_DEMPTY + 2;           // [1] the peer's exact partial winners of a recheck landed (st.async complete_tx)
-constexpr int B_LFULL = B_RX + 1;            // [2]
+constexpr int B_LFULL = B_DEMPTY + 2;        // [2]
 constexpr int B_LEMPTY = B_LFULL + 2;        // [2]
 constexpr int B_PX = B_LEMPTY + 2;           // [2] the peer's partial keys of a step landed here (st.async complete_tx)
 constexpr int NBARS = B_PX + 2;
@@ -126,33 +121,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar_cluster) {   // bar_cluster: mapa() address
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v2(uint32_t addr_cluster, uint32_t a, uint32_t b) {
-  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr_cluster), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr_cluster, uint32_t a) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr_cluster), "r"(a) : "memory");
-}
 // remote store that itself signals the destination CTA's mbarrier (complete_tx): no release fence on the producer side
 __device__ __forceinline__ void st_async_v2(uint32_t addr_cluster, uint32_t a, uint32_t b, uint32_t bar_cluster) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr_cluster),
                "r"(a), "r"(b), "r"(bar_cluster)
                : "memory");
 }
-__device__ __forceinline__ void st_async_u32(uint32_t addr_cluster, uint32_t a, uint32_t bar_cluster) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr_cluster), "r"(a),
-               "r"(bar_cluster)
-               : "memory");
-}
 __device__ __forceinline__ void ld_cluster_2(uint32_t addr_cluster, uint64_t& a, uint64_t& b) {
   asm volatile("ld.shared::cluster.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr_cluster));
-}
-__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
 }
 
 // Bounded wait without a call: a function call inside the update role's setmaxnreg region makes ptxas give up on the
@@ -160,12 +136,6 @@ __device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
 __device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster_nocall(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
     if (++spins == (1u << 22)) __trap();
   }
 }
@@ -178,13 +148,6 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-}
-__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr_cluster) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr_cluster));
-  return v;
 }
 
 // Keys: (dist' + ||x||^2 + thr) is a positive float, so its bits order like an unsigned integer; the low 8 bits carry the
@@ -351,7 +314,14 @@ struct TArgs {
   int need_cost;
   int probe;
   long long* trace;
-  unsigned long long* rstat;   // [2] rechecked rows, candidates evaluated (diagnostics) or NULL
+  unsigned long long* rstat;   // [2] deferred (rechecked) rows, candidates evaluated (diagnostics) or NULL
+  // deferred rows: CTA pair p appends to fix_list[p * seg_cap ..] in step order (a fixed function of the data) and
+  // writes fix_count[p] when it is done; entries below mask_cap also carry their 256-bit candidate mask
+  int2* fix_list;              // {row, label (-1 until k_fix_labels_t)}
+  uint32_t* fix_masks;         // [npairs][mask_cap][8]
+  int32_t* fix_count;          // [npairs]
+  int seg_cap;
+  int mask_cap;
   const B2kLoopState* st;
 };
 
@@ -375,12 +345,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
   uint2* part_s = reinterpret_cast<uint2*>(gbase + OFF_PART);
   float* xoff_s = reinterpret_cast<float*>(gbase + OFF_XOFF);
   int32_t* lab_s = reinterpret_cast<int32_t*>(gbase + OFF_LAB);
-  uint32_t* cand_s = reinterpret_cast<uint32_t*>(gbase + OFF_CAND);
-  float* candT_s = reinterpret_cast<float*>(gbase + OFF_CANDT);
-  uint2* res_s = reinterpret_cast<uint2*>(gbase + OFF_RES);
-  const uint2* resp_s = reinterpret_cast<const uint2*>(gbase + OFF_RESP);
-  uint8_t* flist_s = gbase + OFF_FLIST;
-  float* cnorm_s = reinterpret_cast<float*>(gbase + OFF_CNORM);
   uint8_t* sort_s = gbase + OFF_SORT;
   uint8_t* keytab_s = sort_s + SortT::KEYTAB;
   uint8_t* keyinv_s = sort_s + SortT::KEYINV;
@@ -404,7 +368,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       mbar_init(bar(B_LFULL + i), 1);
       mbar_init(bar(B_LEMPTY + i), N_UPD);
     }
-    mbar_init(bar(B_RX), 1);
     mbar_init(bar(B_PX + 0), 1);
     mbar_init(bar(B_PX + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -416,7 +379,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   for (int j = threadIdx.x; j < 256; j += NTHREADS) {
-    cnorm_s[j] = args.cnorm[j];
     keytab_s[j] = args.keytab[j];
     keyinv_s[j] = args.keyinv[j];
   }
@@ -563,6 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
           const int64_t grow = (int64_t)step_of(it) * TN + col;
           if (grow >= args.n) continue;
           const int label = lab_s[b * TN + col];
+          if (label < 0) continue;   // deferred: k_fix_labels_t writes its min distance
           float s = 0.f;
 #pragma unroll
           for (int i = 0; i < UPL; ++i) {
@@ -708,17 +671,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     float cn4[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) cn4[q] = args.cnorm[jid0 + 8 * q];   // q = 2 h + e
-    const float cn_lane = args.cnorm[rank * KH + (uint32_t)col];     // 32x32b view (candidate enumeration)
     const int cidx = (lane & 24) | ((lane & 3) << 1) | ((lane >> 2) & 1);   // column of the chunk this lane ends up with
     const float thr0 = args.thr[0], thr1 = args.thr[1], thr2 = args.thr[2], thr3 = args.thr[3];
     const uint32_t part_peer0 = mapa_u32(base + OFF_PART, peer);
-    const uint32_t resp_peer0 = mapa_u32(base + OFF_RESP, peer);
     const uint32_t px_peer0 = mapa_u32(bar(B_PX), peer);
-    const uint32_t rx_peer = mapa_u32(bar(B_RX), peer);
     const uint32_t dempty_leader = mapa_u32(bar(B_DEMPTY), 0u);
     const uint32_t src = rank * 4u + (uint32_t)w;
-    uint32_t rxph = 0;
-    unsigned long long n_flag = 0, n_cand = 0;
+    const int pairid = (int)(blockIdx.x >> 1);
+    int2* const seg_list = args.fix_list + (size_t)pairid * (size_t)args.seg_cap;
+    uint32_t* const seg_mask = args.fix_masks + (size_t)pairid * (size_t)args.mask_cap * 8u;
+    int seg_cnt = 0;   // deferred rows of this pair so far (identical in all epilogue threads of both CTAs)
+    unsigned long long n_flag = 0;
     float2 xn_next = make_float2(0.f, 0.f);
     if (nit > 0) {
       const int64_t g0 = (int64_t)step_of(0) * TN + col;
@@ -727,7 +690,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
     for (int it = 0; it < nit; ++it) {
       const int step = step_of(it);
       const int b = it & 1;
-      const int ss = it % NSTEP;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
       const int64_t grow = (int64_t)step * TN + col;
       const bool valid = grow < args.n;
@@ -783,21 +745,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       tc_fence_before();
       if (w == 0) B2K_TR(it, 6);
       asm volatile("bar.sync 1, 128;" ::: "memory");   // this CTA's partials
+      // D of this parity is drained in this CTA (nothing below reads TMEM)
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(dempty_leader + 8u * (uint32_t)b)
+                     : "memory");
+      }
       if (!B2K_PROBE_IS(9)) mbar_wait(bar(B_PX + b), bph);                    // the peer's partials
       if (w == 0) B2K_TR(it, 7);
-      // combine the 8 partials of my column
+      // combine the 8 partials of my column (source s8 = the 32 clusters [32 s8, 32 s8 + 32))
       uint32_t M1 = 0xffffffffu, M2 = 0xffffffffu;
+      uint2 pp[8];
 #pragma unroll
       for (int s8 = 0; s8 < 8; ++s8) {
-        const uint2 p = part_s[(b * 8 + s8) * TN + col];
-        merge2(M1, M2, p.x, p.y);
+        pp[s8] = part_s[(b * 8 + s8) * TN + col];
+        merge2(M1, M2, pp[s8].x, pp[s8].y);
       }
       int label = (int)(M1 & 255u);
       if (B2K_PROBE_IS(9)) label = (col * 2 + (int)rank) & 255;
       const float M1f = __uint_as_float(M1 & 0xffffff00u);
       const bool flag = valid && ((__uint_as_float(M2 & 0xffffff00u) - M1f) < thr) &&
                         !(B2K_PROBE_IS(4) || B2K_PROBE_IS(7) || B2K_PROBE_IS(8) || B2K_PROBE_IS(9) || B2K_PROBE_IS(10) || B2K_PROBE_IS(11) || B2K_PROBE_IS(12));
-      candT_s[col] = M1f + thr;
       const uint32_t fl = __ballot_sync(0xffffffffu, flag);
       if (lane == 0) flagw_s[w] = fl;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -807,146 +774,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
       const int nflag = __popc(fw[0]) + __popc(fw[1]) + __popc(fw[2]) + __popc(fw[3]);
       if (w == 0) B2K_TR(it, 8);
       if (nflag != 0) {
-        // ---- exact recheck of the flagged rows (identical flags in both CTAs).  Every cluster whose approximate distance
-        // is within thr of the best is a candidate; each CTA evaluates the candidates among ITS 128 clusters exactly
-        // (fp32 FMA chains over the row in local / distributed shared memory against the fp32 centres, fixed association,
-        // ascending cluster order, strict '<') and the two partial winners are exchanged with one st.async per row. ----
-        if (threadIdx.x == 0) mbar_expect_tx(bar(B_RX), (uint32_t)nflag * 8u);
-        if (flag) {   // compact list of the flagged columns
+        // ---- deferred rows (identical flags in both CTAs): entry seg_cnt + (rank of the column among the step's flagged
+        // columns), written by the row's owner.  Candidates = every cluster whose approximate distance may be within thr of
+        // the best, as a superset read off the 8 partials: a 32-cluster group whose best key is above best + thr has none,
+        // one whose second key is above it has exactly its best, otherwise the whole group is tested. ----
+        if (flag && (uint32_t)(col >> 6) == rank) {
           int pos = __popc(fl & ((1u << lane) - 1u));
 #pragma unroll
           for (int q2 = 0; q2 < 3; ++q2)
             if (q2 < w) pos += __popc(fw[q2]);
-          flist_s[pos] = (uint8_t)col;
-        }
-        // (1) candidate masks of this CTA's clusters from D (32x32b view: lane = cluster)
-#pragma unroll 1
-        for (int wd = 0; wd < 4; ++wd) {
-          uint32_t m = fw[wd];
-          while (m) {
-            const int c = wd * 32 + (__ffs(m) - 1);
-            m &= m - 1;
-            const uint32_t dv = tmem_ld_x1(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(D_OFF + b * TN + c));
-            tmem_wait_ld();
-            const float dist = fmaf(-2.f, __uint_as_float(dv), cn_lane) + xoff_s[c];
-            const uint32_t bm = __ballot_sync(0xffffffffu, dist <= candT_s[c]);
-            if (lane == 0) cand_s[c * 4 + w] = bm;
+          const int e = seg_cnt + pos;
+          seg_list[e] = make_int2((int)grow, -1);
+          if (e < args.mask_cap) {
+            const float T = M1f + thr;
+            uint32_t mk[8];
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+              const bool any = __uint_as_float(pp[s8].x & 0xffffff00u) <= T;
+              const bool two = __uint_as_float(pp[s8].y & 0xffffff00u) <= T;
+              mk[s8] = any ? (two ? 0xffffffffu : (1u << (pp[s8].x & 31u))) : 0u;
+            }
+            uint4* dst = reinterpret_cast<uint4*>(seg_mask + (size_t)e * 8u);
+            dst[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            dst[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
           }
+          ++n_flag;
         }
-        tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        seg_cnt += nflag;
         if (w == 0) B2K_TR(it, 9);
       }
-      // D of this parity is drained in this CTA
-      if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(dempty_leader + 8u * (uint32_t)b)
-                     : "memory");
-      }
-      if (nflag != 0) {
-        // (2) exact evaluation, four rows per warp pass: lane group g = lane >> 3 takes one row, its 8 lanes split the
-        // columns (chunk t, 16-byte unit lane & 7)
-        const int sl = lane & 7;
-#pragma unroll 1
-        for (int i0 = w * 4; i0 < nflag; i0 += 16) {
-          const int i = i0 + (lane >> 3);
-          const bool act = i < nflag;
-          const int c = (int)flist_s[act ? i : 0];
-          const int lrow = c & 63;
-          const bool local = (uint32_t)(c >> 6) == rank;
-          const uint32_t xa0 = ring + (uint32_t)((ss * NCH) * SLOT_BYTES + lrow * 128) + (uint32_t)((sl ^ (lrow & 7)) << 4);
-          const uint32_t xr0 = mapa_u32(xa0, peer);
-          float4 xv[NCH];
-#pragma unroll
-          for (int t = 0; t < NCH; ++t) {
-            if (local) xv[t] = lds128(xa0 + (uint32_t)(t * SLOT_BYTES));
-            else xv[t] = ld_cluster_f4(xr0 + (uint32_t)(t * SLOT_BYTES));
-          }
-          float best = __int_as_float(0x7f800000);
-          int bj = -1;
-          int wi = -1;
-          uint32_t bmw = 0;
-          auto next_cand = [&]() -> int {   // this CTA's candidates of the row in ascending cluster order, -1 at the end
-            if (!act) return -1;
-            for (;;) {
-              while (bmw == 0u && wi < 3) { ++wi; bmw = cand_s[c * 4 + wi]; }
-              if (bmw == 0u) return -1;
-              const int j = (int)rank * KH + wi * 32 + (__ffs(bmw) - 1);
-              bmw &= bmw - 1;
-              if (j < args.k) return j;
-            }
-          };
-          for (;;) {   // two candidates per trip: both centre rows' loads are in flight together
-            const int ja = next_cand();
-            const int jb = ja >= 0 ? next_cand() : -1;
-            if (!__any_sync(0xffffffffu, ja >= 0)) break;
-            float dota = 0.f, dotb = 0.f;
-            if (ja >= 0) {
-              const float* pa = args.C32 + (size_t)ja * args.d + sl * 4;
-              const float* pb = args.C32 + (size_t)(jb >= 0 ? jb : ja) * args.d + sl * 4;
-#pragma unroll
-              for (int t = 0; t < NCH; ++t) {
-                if (t * 32 + sl * 4 < args.d) {
-                  const float4 ca = __ldg(reinterpret_cast<const float4*>(pa + t * 32));
-                  const float4 cb = __ldg(reinterpret_cast<const float4*>(pb + t * 32));
-                  dota = fmaf(xv[t].x, ca.x, fmaf(xv[t].y, ca.y, fmaf(xv[t].z, ca.z, fmaf(xv[t].w, ca.w, dota))));
-                  dotb = fmaf(xv[t].x, cb.x, fmaf(xv[t].y, cb.y, fmaf(xv[t].z, cb.z, fmaf(xv[t].w, cb.w, dotb))));
-                }
-              }
-            }
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-              dota += __shfl_xor_sync(0xffffffffu, dota, o);
-              dotb += __shfl_xor_sync(0xffffffffu, dotb, o);
-            }
-            if (ja >= 0) {
-              const float da = fmaf(-2.f, dota, cnorm_s[ja]);
-              if (da < best) { best = da; bj = ja; }
-              if (sl == 0) ++n_cand;
-            }
-            if (jb >= 0) {
-              const float db = fmaf(-2.f, dotb, cnorm_s[jb]);
-              if (db < best) { best = db; bj = jb; }
-              if (sl == 0) ++n_cand;
-            }
-          }
-          if (act && sl == 0) {
-            res_s[c] = make_uint2(__float_as_uint(best), (uint32_t)bj);
-            st_async_v2(resp_peer0 + (uint32_t)c * 8u, __float_as_uint(best), (uint32_t)bj, rx_peer);
-            if (local) ++n_flag;
-          }
-        }
-        if (w == 0) B2K_TR(it, 13);
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // this CTA's partial winners
-        mbar_wait(bar(B_RX), rxph);                       // the peer's
-        if (w == 0) B2K_TR(it, 15);
-        rxph ^= 1u;
-        if (flag) {
-          const uint2 mine = res_s[col], theirs = resp_s[col];
-          const uint2 lo = rank == 0 ? mine : theirs, hi = rank == 0 ? theirs : mine;   // lo: clusters 0..127
-          const float vlo = __uint_as_float(lo.x), vhi = __uint_as_float(hi.x);
-          const int jlo = (int)lo.y, jhi = (int)hi.y;
-          int f = jlo;
-          if (jlo < 0 || (jhi >= 0 && vhi < vlo)) f = jhi;
-          if (f >= 0) label = f;
-        }
-      }
-      // ---- publish the labels: the update warps find their rows themselves (invalid rows: -1) ----
+      if (flag) label = -1;
+      // ---- publish the labels: the update warps find their rows themselves (invalid and deferred rows: -1) ----
       lab_s[b * TN + col] = valid ? label : -1;
-      if (valid && (uint32_t)(col >> 6) == rank && args.labels_out != nullptr) args.labels_out[grow] = label;
+      if (valid && label >= 0 && (uint32_t)(col >> 6) == rank && args.labels_out != nullptr) args.labels_out[grow] = label;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 0) mbar_arrive(bar(B_LFULL + b));
       if (w == 0) B2K_TR(it, 10);
     }
-    if (args.rstat != nullptr) {   // per-lane counters (counted in the lane-group leaders)
+    if (threadIdx.x == 0 && rank == 0) args.fix_count[pairid] = seg_cnt;
+    if (args.rstat != nullptr) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        n_flag += __shfl_xor_sync(0xffffffffu, n_flag, o);
-        n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
-      }
-      if (lane == 0 && (n_flag | n_cand) != 0ull) {
-        atomicAdd(args.rstat + 0, n_flag);
-        atomicAdd(args.rstat + 1, n_cand);
-      }
+      for (int o = 16; o > 0; o >>= 1) n_flag += __shfl_xor_sync(0xffffffffu, n_flag, o);
+      if (lane == 0 && n_flag != 0ull) atomicAdd(args.rstat + 0, n_flag);
     }
   }
 
@@ -967,10 +836,227 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_t(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// fix-up of the deferred rows
+// ------------------------------------------------------------------------------------------------
+struct FixArgs {
+  const float* X;
+  int64_t n;
+  int d, k;
+  const float* C32;            // [k][d]
+  const float* cnorm;          // [256] ||c||^2 (fp32 centres)
+  int2* list;
+  const uint32_t* masks;
+  const int32_t* count;
+  int npairs, seg_cap, mask_cap;
+  int32_t* labels_out;         // or NULL
+  float* mind_out;             // or NULL
+  int need_cost;
+  double* cost_out;            // [gridDim.x] (always written)
+  unsigned long long* rstat;   // or NULL
+  float* partial;              // k_fix_accum_t: the extra slot's [k][d] sums
+  int32_t* counts_out;         // and its [k] counts
+  const B2kLoopState* st;
+};
+constexpr int FIX_WARPS = 8;
+constexpr int FIX_MAXP = 256;
+
+// One warp per deferred row: exact argmin over the row's candidates.  d(j) = ||c_j||^2 - 2 x.c_j with the dot product as
+// one fp32 FMA chain per lane (columns lane*4 + 128 i) and a fixed 5-level shuffle tree; candidates in ascending
+// cluster order with strict '<' (lowest index wins ties).  Entries beyond the mask capacity test every cluster.
+__global__ void __launch_bounds__(FIX_WARPS * 32) k_fix_labels_t(const FixArgs f) {
+  if (f.st != nullptr && f.st->done) return;
+  __shared__ int pre[FIX_MAXP + 1];
+  __shared__ double cost_w[FIX_WARPS];
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int p = 0; p < f.npairs; ++p) {
+      pre[p] = a;
+      a += f.count[p];
+    }
+    pre[f.npairs] = a;
+  }
+  __syncthreads();
+  const int M = pre[f.npairs];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double cost = 0.0;
+  unsigned long long ncand = 0;
+  for (int i = (int)blockIdx.x * FIX_WARPS + warp; i < M; i += (int)gridDim.x * FIX_WARPS) {
+    int p = 0;   // segment of entry i = the number of segments that end at or before i (ends are non-decreasing)
+    for (int b0 = 0; b0 < f.npairs; b0 += 32) {
+      const int q = b0 + lane;
+      p += __popc(__ballot_sync(0xffffffffu, q < f.npairs && pre[q + 1] <= i));
+    }
+    const int e = i - pre[p];
+    int2* ent = f.list + (size_t)p * (size_t)f.seg_cap + e;
+    const int64_t row = (int64_t)ent->x;
+    uint32_t mw = 0xffffffffu;
+    if (e < f.mask_cap && lane < 8) mw = f.masks[((size_t)p * (size_t)f.mask_cap + (size_t)e) * 8u + (uint32_t)lane];
+    float4 xv[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int cc = lane * 4 + 128 * t;
+      xv[t] = cc < f.d ? __ldg(reinterpret_cast<const float4*>(f.X + (size_t)row * f.d + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float best = __int_as_float(0x7f800000);
+    int bj = -1;
+    for (int pass = 0; pass < 2 && bj < 0; ++pass) {   // pass 1 (every cluster) only if the mask held no valid candidate
+      int wi = -1;
+      uint32_t bm = 0;
+      auto next_cand = [&]() -> int {   // ascending cluster order, -1 at the end (warp-uniform)
+        for (;;) {
+          while (bm == 0u && wi < 7) {
+            ++wi;
+            bm = pass == 0 ? __shfl_sync(0xffffffffu, mw, wi) : 0xffffffffu;
+          }
+          if (bm == 0u) return -1;
+          const int j = wi * 32 + (__ffs(bm) - 1);
+          bm &= bm - 1;
+          if (j < f.k) return j;
+          bm = 0u;   // clusters are ascending: nothing valid is left in this word
+        }
+      };
+      for (;;) {   // two candidates per trip: both centre rows' loads are in flight together
+        const int ja = next_cand();
+        if (ja < 0) break;
+        const int jb = next_cand();
+        const int jb2 = jb >= 0 ? jb : ja;
+        float dota = 0.f, dotb = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int cc = lane * 4 + 128 * t;
+          if (cc < f.d) {
+            const float4 ca = __ldg(reinterpret_cast<const float4*>(f.C32 + (size_t)ja * f.d + cc));
+            const float4 cb = __ldg(reinterpret_cast<const float4*>(f.C32 + (size_t)jb2 * f.d + cc));
+            dota = fmaf(xv[t].x, ca.x, fmaf(xv[t].y, ca.y, fmaf(xv[t].z, ca.z, fmaf(xv[t].w, ca.w, dota))));
+            dotb = fmaf(xv[t].x, cb.x, fmaf(xv[t].y, cb.y, fmaf(xv[t].z, cb.z, fmaf(xv[t].w, cb.w, dotb))));
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dota += __shfl_xor_sync(0xffffffffu, dota, o);
+          dotb += __shfl_xor_sync(0xffffffffu, dotb, o);
+        }
+        const float da = fmaf(-2.f, dota, f.cnorm[ja]);
+        if (da < best) { best = da; bj = ja; }
+        ++ncand;
+        if (jb >= 0) {
+          const float db = fmaf(-2.f, dotb, f.cnorm[jb]);
+          if (db < best) { best = db; bj = jb; }
+          ++ncand;
+        }
+      }
+    }
+    if (lane == 0) {
+      ent->y = bj;
+      if (f.labels_out != nullptr) f.labels_out[row] = bj;
+    }
+    if (f.need_cost) {   // exact min distance sum (x - c)^2, as the update role computes it for the other rows
+      float s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int cc = lane * 4 + 128 * t;
+        if (cc < f.d) {
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(f.C32 + (size_t)bj * f.d + cc));
+          const float dx = xv[t].x - cv.x, dy = xv[t].y - cv.y, dz = xv[t].z - cv.z, dw = xv[t].w - cv.w;
+          s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, s2))));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == 0) {
+        if (f.mind_out != nullptr) f.mind_out[row] = s2;
+        cost += (double)s2;
+      }
+    }
+  }
+  if (lane == 0) cost_w[warp] = cost;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    for (int w2 = 0; w2 < FIX_WARPS; ++w2) c += cost_w[w2];
+    f.cost_out[blockIdx.x] = c;
+  }
+  if (f.rstat != nullptr && lane == 0 && ncand != 0ull) atomicAdd(f.rstat + 1, ncand);
+}
+
+// One CTA per cluster, thread = column: scans the segments in order, compacts the rows labelled with its cluster into
+// shared memory (list order) and adds them with eight row loads in flight — the order of the additions is a fixed
+// function of the data (segments in pair order, entries in step order), hence deterministic.
+constexpr int ACC_CH = 1024;   // entries per scan step (4 per thread)
+constexpr int FIX_SLOTS = 4;   // partial-sum slots of the deferred rows: slot q takes the segments p = q (mod 4)
+__global__ void __launch_bounds__(256) k_fix_accum_t(const FixArgs f) {
+  if (f.st != nullptr && f.st->done) return;
+  __shared__ int buf[ACC_CH];
+  __shared__ int wsum[8];
+  const int j = (int)blockIdx.x;
+  const int slot = (int)blockIdx.y;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float acc = 0.f;
+  int cnt = 0;
+  for (int p = slot; p < f.npairs; p += FIX_SLOTS) {
+    const int c = f.count[p];
+    const int2* seg = f.list + (size_t)p * (size_t)f.seg_cap;
+    for (int e0 = 0; e0 < c; e0 += ACC_CH) {
+      const int eb = e0 + tid * 4;
+      int2 en[4];
+      if (eb + 3 < c) {   // 32 contiguous bytes (segment bases are 256-byte aligned)
+        const int4 a0 = *reinterpret_cast<const int4*>(seg + eb);
+        const int4 a1 = *reinterpret_cast<const int4*>(seg + eb + 2);
+        en[0] = make_int2(a0.x, a0.y);
+        en[1] = make_int2(a0.z, a0.w);
+        en[2] = make_int2(a1.x, a1.y);
+        en[3] = make_int2(a1.z, a1.w);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) en[q] = eb + q < c ? seg[eb + q] : make_int2(-1, -1);
+      }
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mine += en[q].y == j ? 1 : 0;
+      int incl = mine;   // inclusive scan over the warp, then over the 8 warps
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      int off = incl - mine, total = 0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        const int v = wsum[w8];
+        if (w8 < warp) off += v;
+        total += v;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (en[q].y == j) buf[off++] = en[q].x;
+      __syncthreads();
+      if (tid < f.d) {
+        const float* xc = f.X + tid;
+        for (int q = 0; q < total; q += 16) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = q + u < total ? __ldg(xc + (size_t)buf[q + u] * f.d) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc += v[u];
+        }
+      }
+      cnt += total;
+      __syncthreads();
+    }
+  }
+  if (tid < f.d) f.partial[((size_t)slot * f.k + j) * f.d + tid] = acc;
+  if (tid == 0) f.counts_out[(size_t)slot * f.k + j] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TLayout {
-  size_t off_ct, off_cnorm, off_thr, off_tab, off_rstat, off_partials, off_counts, off_cost, off_xnorm, total;
+  size_t off_ct, off_cnorm, off_thr, off_tab, off_rstat, off_partials, off_counts, off_cost, off_xnorm, off_fixlist, off_fixmask,
+      off_fixcnt, total;
+  int npairs, seg_cap, mask_cap;
 };
 TLayout t_layout(const B2kFusedPlan& p, int64_t n, int k, int d) {
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -983,8 +1069,18 @@ TLayout t_layout(const B2kFusedPlan& p, int64_t n, int k, int d) {
   L.off_rstat = o; o = al(o + 16);
   L.off_partials = o; o = al(o + (size_t)p.P * k * d * 4);
   L.off_counts = o; o = al(o + (size_t)p.P * k * 4);
-  L.off_cost = o; o = al(o + (size_t)p.grid * 8);
+  L.off_cost = o; o = al(o + (size_t)p.Pc * 8);
   L.off_xnorm = o; o = al(o + (size_t)(n > 0 ? n : 1) * 8);
+  // deferred-row segments: a pair can defer every row it sees; candidate masks for the first 1/4 of a segment (entries
+  // beyond that are decided against every cluster)
+  L.npairs = p.grid / 2;
+  const int64_t nsteps = (n + TN - 1) / TN;
+  const int64_t nit_max = (nsteps + L.npairs - 1) / L.npairs;
+  L.seg_cap = (int)(nit_max * TN);
+  L.mask_cap = (int)std::min<int64_t>(L.seg_cap, ((nit_max + 3) / 4) * TN);
+  L.off_fixlist = o; o = al(o + (size_t)L.npairs * L.seg_cap * 8);
+  L.off_fixmask = o; o = al(o + (size_t)L.npairs * L.mask_cap * 32);
+  L.off_fixcnt = o; o = al(o + (size_t)L.npairs * 4);
   L.total = o;
   return L;
 }
@@ -1030,7 +1126,8 @@ int b2k_fused_t_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan) 
   if (nsteps * 2 < grid) grid = (int)nsteps * 2;
   if (grid < 2) grid = 2;
   plan->grid = grid;
-  plan->P = grid / 2;
+  plan->P = grid / 2 + FIX_SLOTS;             // one slot per CTA pair + the deferred rows' slots (k_fix_accum_t)
+  plan->Pc = grid + 8 * ctx->sm_count;        // cost partials: one per CTA + one per k_fix_labels_t CTA
   plan->scratch_bytes = t_layout(*plan, n, k, d).total;
   return B2K_OK;
 }
@@ -1105,7 +1202,13 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   }
 #endif
   a.rstat = reinterpret_cast<unsigned long long*>(b + L.off_rstat);
+  a.fix_list = reinterpret_cast<int2*>(b + L.off_fixlist);
+  a.fix_masks = reinterpret_cast<uint32_t*>(b + L.off_fixmask);
+  a.fix_count = reinterpret_cast<int32_t*>(b + L.off_fixcnt);
+  a.seg_cap = L.seg_cap;
+  a.mask_cap = L.mask_cap;
   a.st = st;
+  if (L.npairs > FIX_MAXP) return b2k_fail(ctx, B2K_ERR_STATE, "fused_t: more CTA pairs than the fix-up kernels index");
 
   int rc;
   if (plan.DP == 128) rc = do_update ? launch_t<4, true>(ctx, plan.grid, mx, a, s) : launch_t<4, false>(ctx, plan.grid, mx, a, s);
@@ -1113,5 +1216,35 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   B2K_TRY(rc);
   ctx->stats.kernel_launches++;
   ctx->stats.fused_tc_launches++;
+
+  // the deferred rows: exact labels (+ min distance / cost), then their contribution to the sums (the last FIX_SLOTS slots)
+  FixArgs f{};
+  f.X = X;
+  f.n = n;
+  f.d = d;
+  f.k = k;
+  f.C32 = C;
+  f.cnorm = cnorm;
+  f.list = a.fix_list;
+  f.masks = a.fix_masks;
+  f.count = a.fix_count;
+  f.npairs = L.npairs;
+  f.seg_cap = L.seg_cap;
+  f.mask_cap = L.mask_cap;
+  f.labels_out = labels_out;
+  f.mind_out = mindist_out;
+  f.need_cost = need_cost ? 1 : 0;
+  f.cost_out = a.cost_partials + plan.grid;
+  f.rstat = a.rstat;
+  f.partial = a.partials + (size_t)(plan.P - FIX_SLOTS) * k * d;
+  f.counts_out = a.counts + (size_t)(plan.P - FIX_SLOTS) * k;
+  f.st = st;
+  k_fix_labels_t<<<plan.Pc - plan.grid, FIX_WARPS * 32, 0, s>>>(f);
+  ctx->stats.kernel_launches++;
+  if (do_update) {
+    k_fix_accum_t<<<dim3((unsigned)k, FIX_SLOTS), 256, 0, s>>>(f);
+    ctx->stats.kernel_launches++;
+  }
+  B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
 }

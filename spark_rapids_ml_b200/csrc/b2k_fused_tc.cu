@@ -1018,6 +1018,7 @@ int b2k_fused_plan(b2k_ctx* ctx, int64_t n, int d, int k, B2kFusedPlan* plan) {
   }
   plan->grid = grid;
   plan->P = grid;
+  plan->Pc = grid;
   plan->scratch_bytes = plan_layout(*plan, k, d).total;
   return B2K_OK;
 }

@@ -296,6 +296,16 @@ int b2k_launch_update_generic(b2k_ctx* ctx, const float* X, int64_t n, int d, co
 // ------------------------------------------------------------------------------------------------
 // R = fixed-order sum over partials (double): [k*d sums | k counts | cost]
 // ------------------------------------------------------------------------------------------------
+// sum of m doubles by one warp in a FIXED order (lane-strided chains, then a shuffle tree): deterministic
+__device__ __forceinline__ double warp_fold_f64(const double* __restrict__ in, int m) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0;
+  for (int i = lane; i < m; i += 32) a += in[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials,
                                                          const int32_t* __restrict__ counts, int P,
                                                          const double* __restrict__ cost_partials, int Pc,
@@ -303,6 +313,13 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
                                                          const B2kLoopState* st) {
   B2K_EARLY_EXIT(st);
   size_t kd = (size_t)k * d;
+  if (blockIdx.x == gridDim.x - 1) {   // the extra block: the cost partials, one warp
+    if (threadIdx.x < 32) {
+      const double a = cost_partials ? warp_fold_f64(cost_partials, Pc) : 0.0;
+      if (threadIdx.x == 0) R[kd + k] = a;
+    }
+    return;
+  }
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < kd) {
     double a = 0.0;
@@ -313,11 +330,6 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
     double a = 0.0;
     for (int p = 0; p < P; ++p) a += (double)counts[(size_t)p * k + j];
     R[e] = a;
-  } else if (e == kd + k) {
-    double a = 0.0;
-    if (cost_partials)
-      for (int p = 0; p < Pc; ++p) a += cost_partials[p];
-    R[e] = a;
   }
 }
 
@@ -325,7 +337,7 @@ int b2k_launch_reduce_partials(b2k_ctx* ctx, const float* partials, const int32_
                                const double* cost_partials, int P, int Pc, int k, int d, double* R,
                                const B2kLoopState* st, cudaStream_t s) {
   size_t len = b2k_reduced_len(k, d);
-  unsigned blocks = (unsigned)((len + 255) / 256);
+  unsigned blocks = (unsigned)((len + 255) / 256) + 1;   // + the cost block
   k_reduce_partials<<<blocks, 256, 0, s>>>(partials, counts, P, cost_partials, Pc, k, d, R, st);
   ctx->stats.kernel_launches++;
   B2K_CUDA_OK(ctx, cudaGetLastError());
@@ -408,10 +420,9 @@ __global__ void __launch_bounds__(256) k_block_sums(const float* __restrict__ v,
   if (threadIdx.x == 0) block_out[blockIdx.x] = red[0];
 }
 __global__ void k_fold_f64(const double* __restrict__ in, int m, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double a = 0.0;
-    for (int i = 0; i < m; ++i) a += in[i];
-    out[0] = a;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const double a = warp_fold_f64(in, m);
+    if (threadIdx.x == 0) out[0] = a;
   }
 }
 

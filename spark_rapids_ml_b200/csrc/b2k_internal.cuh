@@ -135,7 +135,8 @@ struct B2kFusedPlan {
   int grid = 0;              // persistent CTAs
   int pair = 0;              // 1: CTA-pair (tcgen05 cta_group::2) instantiation, grid is even
   int variant = 0;           // 0: b2k_fused_tc.cu (k <= 128, d <= 128, 3xTF32); 1: b2k_fused_t.cu (k, d <= 256, 1xTF32 + recheck)
-  int P = 0;                 // partial-sum slots the pass writes (variant 0: grid, variant 1: grid / 2 = CTA pairs)
+  int P = 0;                 // partial-sum slots the pass writes (variant 0: grid; variant 1: CTA pairs + 1 for the deferred rows)
+  int Pc = 0;                // cost partials the pass writes (variant 0: grid; variant 1: grid + fix-up CTAs)
   size_t scratch_bytes = 0;  // centre operands/cnorm + partials/counts/cost (+ row norms, variant 1)
 };
 bool b2k_fused_supported(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X);

@@ -20,7 +20,8 @@ import os
 if os.environ.get("B2K_PROBE_N"):
     ctx.set_option("probe", int(os.environ["B2K_PROBE_N"]))
 Cw = C.clone()
-ctx.kmeans_lloyd(X, Cw, 10 if len(sys.argv) > 1 else 2, -1.0)   # settle the centres before tracing a bad start
+if not (len(sys.argv) > 2 and sys.argv[2] == "raw"):   # "first_k raw": trace the very first iteration of the bad start
+    ctx.kmeans_lloyd(X, Cw, 10 if len(sys.argv) > 1 else 2, -1.0)   # settle the centres before tracing a bad start
 ctx.set_option("profile_fused", 1)
 ctx.set_option("collect_recheck", 1)
 ctx.kmeans_lloyd(X, Cw, 1, -1.0)
