@@ -104,6 +104,9 @@ typedef struct b2k_stats {
                                   whose approximate margin was below the proven error bound and were re-decided
                                   exactly (summed over its passes; 0 unless option "collect_recheck" is 1) */
   int64_t recheck_candidates;  /* ... exact candidate distances evaluated for them */
+  int64_t path_switch_iter;    /* iteration from which the last Lloyd loop left the large-shape tcgen05 kernel for the
+                                  generic kernels because most rows needed the exact fix-up (option "adaptive_path",
+                                  default 1; only with kernel_path = auto); -1 = it did not */
 } b2k_stats;
 
 int b2k_version(void);
@@ -115,7 +118,7 @@ int b2k_ctx_destroy(b2k_ctx* ctx);
  * around the partial fold, the allreduce and finalize), "check_every" (iterations between host
  * convergence polls, default 4), "grid_limit" (cap on persistent CTAs, 0 = #SMs), "variant_t" (1 = route every shape with k, d <= 256 through the
  * large-shape kernel b2k_fused_t.cu; default 0 = only shapes the 3xTF32 kernel does not cover), "collect_recheck"
- * (1 = lloyd/assign synchronise and fill b2k_stats.recheck_*), "ingest_threads" (host threads of the pageable -> pinned
+ * (1 = lloyd/assign synchronise and fill b2k_stats.recheck_*), "adaptive_path" (see b2k_stats.path_switch_iter), "ingest_threads" (host threads of the pageable -> pinned
  * staging copy of b2k_ingest_append; 0 = default: 4, capped by half of the CPUs the process may use), "pair" (1 = use the
  * CTA-pair tcgen05 cta_group::2 kernel where instantiated, default 1); diagnostic builds only (`make trace` ->
  * libb2kmeans_trace.so, `-DB2K_PROBE=1`): "profile_fused" (0/1; the product build rejects it with

@@ -76,6 +76,7 @@ class Stats(ctypes.Structure):
         ("last_finalize_ms", ctypes.c_double),
         ("recheck_rows", ctypes.c_int64),
         ("recheck_candidates", ctypes.c_int64),
+        ("path_switch_iter", ctypes.c_int64),
     ]
 
 

@@ -100,6 +100,8 @@ extern "C" int b2k_ctx_set_option(b2k_ctx* ctx, const char* key, int64_t value) 
     ctx->probe = (int)value;
   } else if (k == "pair") {
     ctx->pair = value ? 1 : 0;
+  } else if (k == "adaptive_path") {
+    ctx->adaptive_path = value ? 1 : 0;
   } else if (k == "variant_t") {
     ctx->force_variant_t = value ? 1 : 0;
   } else if (k == "ingest_threads") {
@@ -225,28 +227,31 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
 
   LoopBuffers B{};
   size_t gen_bytes = 0;
-  if (fused) {
-    B2K_TRY(b2k_fused_plan(ctx, n, d, k, &B.plan));
-  } else {
-    gen_bytes = b2k_update_generic_scratch(ctx, n, d, k, &B.P);
-  }
+  if (fused) B2K_TRY(b2k_fused_plan(ctx, n, d, k, &B.plan));
+  // The large-shape kernel (1xTF32 screening) hands near-tie rows to an exact fix-up; on data where most rows are
+  // near-ties (e.g. uniform noise in 256 dimensions) the generic kernels are several times faster, so the loop may
+  // switch to them between bursts.  The choice is local to the rank: both paths fill the same R buffer.
+  const bool can_switch = fused && B.plan.variant == 1 && ctx->adaptive_path && ctx->kernel_path == B2K_PATH_AUTO;
+  const bool need_generic = !fused || can_switch;
+  if (need_generic) gen_bytes = b2k_update_generic_scratch(ctx, n, d, k, &B.P);
   const size_t rlen = b2k_reduced_len(k, d);
   size_t total = 4096 + align_up(rlen * 8, 256) + align_up((size_t)k * 8, 256) + align_up((size_t)k * 4, 256) +
-                 (fused ? align_up(B.plan.scratch_bytes, 1024) + 1024
-                        : align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 1024);
+                 (fused ? align_up(B.plan.scratch_bytes, 1024) + 2048 : 0) +
+                 (need_generic ? align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 4096 : 0);
   B2K_TRY(b2k_scratch_reserve(ctx, total));
   Arena A(ctx->scratch);
   B.st = A.take<B2kLoopState>(1);
   B.R = A.take<double>(rlen);
   B.shift_scratch = A.take<double>(k);
   B.cnorm = A.take<float>(k);
-  if (fused) {
-    A.off = align_up(A.off, 1024);
-    B.plan_scratch = A.base + A.off;
-  } else {
+  if (need_generic) {
     B.labels = A.take<int32_t>(n > 0 ? n : 1);
     B.partials = A.take<float>((size_t)B.P * k * d);
     B.counts = A.take<int32_t>((size_t)B.P * k);
+  }
+  if (fused) {
+    A.off = align_up(A.off, 1024);
+    B.plan_scratch = A.base + A.off;
   }
 
   B2kLoopState init{};
@@ -257,6 +262,8 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   init.tol = tol;
   init.shift = 0.0;
   init.cost = 0.0;
+  init.fix_rows_cum = 0;
+  init.fix_cands_cum = 0;
   *ctx->h_state = init;
   B2K_CUDA_OK(ctx, cudaMemcpyAsync(B.st, ctx->h_state, sizeof(B2kLoopState), cudaMemcpyHostToDevice, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));  // h_state is reused as the D2H mirror below
@@ -285,13 +292,17 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   // makes an over-enqueued burst free).  The read-backs alternate between two pinned mirrors.
   int launched = 0, slot = 0;
   bool done = (max_iter == 0), have_pending = false;
+  bool fused_now = fused;
+  int burst_iters[2] = {0, 0};
+  unsigned long long seen_rows = 0, seen_cands = 0;
+  ctx->stats.path_switch_iter = -1;
   B2kLoopState* mirror = ctx->h_state;
   int last_slot = 0;
   while (!done && launched < max_iter) {
     int burst = std::min(ctx->check_every, max_iter - launched);
     for (int b = 0; b < burst; ++b) {
       cudaEvent_t* e = ctx->time_kernels ? &ev[(size_t)launched * nev_per_it] : nullptr;
-      if (fused) {
+      if (fused_now) {
         if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[0], s));
         // cluster sizes of the previous iteration (R = [k*d sums | k counts | cost]) drive the update-warp balancing
         B2K_TRY(b2k_launch_fused(ctx, B.plan, B.plan_scratch, X, n, d, C, k, nullptr, nullptr, true, B.st, s,
@@ -318,11 +329,27 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
       ++launched;
     }
     if (t_first_burst == 0.0) t_first_burst = since(t_loop);
+    burst_iters[slot] = fused_now ? burst : 0;
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(&mirror[slot], B.st, sizeof(B2kLoopState), cudaMemcpyDeviceToHost, s));
     B2K_CUDA_OK(ctx, cudaEventRecord(poll_ev[slot], s));
     if (have_pending) {   // the flag of the PREVIOUS burst, while this one is already queued
       B2K_CUDA_OK(ctx, cudaEventSynchronize(poll_ev[slot ^ 1]));
-      done = mirror[slot ^ 1].done != 0;
+      const B2kLoopState& m = mirror[slot ^ 1];
+      done = m.done != 0;
+      if (can_switch && fused_now && burst_iters[slot ^ 1] > 0 && n > 0) {
+        // measured on B200 (tools/fix_split.py, k = d = 256): the fix-up costs ~0.14 ns per candidate distance + ~0.85 ns
+        // per deferred row; the generic kernels ~6.4 ns per row more than the fused pass (scaled here by k d)
+        const double it = (double)burst_iters[slot ^ 1];
+        const double rows_per_row = (double)(m.fix_rows_cum - seen_rows) / it / (double)n;
+        const double cands_per_row = (double)(m.fix_cands_cum - seen_cands) / it / (double)n;
+        const double generic_extra_ns = 6.4 * ((double)k * (double)d) / 65536.0;
+        if (0.14 * cands_per_row + 0.85 * rows_per_row > generic_extra_ns) {
+          fused_now = false;
+          ctx->stats.path_switch_iter = launched;
+        }
+      }
+      seen_rows = m.fix_rows_cum;
+      seen_cands = m.fix_cands_cum;
     }
     last_slot = slot;
     have_pending = true;
@@ -365,6 +392,8 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
     cudaEventDestroy(loop1);
   }
   ctx->stats.last_n_iter = ctx->h_state->iter;
+  ctx->lloyd_switched = (fused && !fused_now) ? 1 : 0;
+  if (ctx->lloyd_switched) ctx->stats.last_path = B2K_PATH_GENERIC;
   if (fused && ctx->collect_recheck && max_iter > 0) {
     unsigned long long rs[2];
     B2K_TRY(b2k_fused_recheck_stats(ctx, B.plan, B.plan_scratch, n, k, d, rs, s));
@@ -793,9 +822,14 @@ extern "C" int b2k_kmeans_fit(b2k_ctx* ctx, const float* X, int64_t n_local, int
   }
   B2K_TRY(lloyd_impl(ctx, X, n_local, d, k, centers_out, max_iter, tol, n_iter_out, nullptr, s));
   if (inertia_out) {
-    B2K_TRY(b2k_scratch_reserve(ctx, 4096 + assign_scratch_bound(ctx, n_local, d, k, X)));
+    // the inertia pass follows the Lloyd loop's choice of path (see lloyd_impl: adaptive_path)
+    const int saved_path = ctx->kernel_path;
+    if (ctx->lloyd_switched) ctx->kernel_path = B2K_PATH_GENERIC;
+    int rc = b2k_scratch_reserve(ctx, 4096 + assign_scratch_bound(ctx, n_local, d, k, X));
     double* cost_dev = reinterpret_cast<double*>(ctx->scratch);
-    B2K_TRY(assign_impl(ctx, X, n_local, d, centers_out, k, nullptr, nullptr, cost_dev, 1024, s));
+    if (rc == B2K_OK) rc = assign_impl(ctx, X, n_local, d, centers_out, k, nullptr, nullptr, cost_dev, 1024, s);
+    ctx->kernel_path = saved_path;
+    B2K_TRY(rc);
     if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, cost_dev, 1, s));
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(inertia_out, cost_dev, 8, cudaMemcpyDeviceToHost, s));
     B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));

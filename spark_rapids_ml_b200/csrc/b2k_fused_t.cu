@@ -856,6 +856,7 @@ struct FixArgs {
   float* partial;              // k_fix_accum_t: the extra slot's [k][d] sums
   int32_t* counts_out;         // and its [k] counts
   const B2kLoopState* st;
+  B2kLoopState* st_w;          // same object: k_fix_accum_t publishes the cumulative fix-up counters to the host's poll
 };
 constexpr int FIX_WARPS = 8;
 constexpr int FIX_MAXP = 256;
@@ -1048,6 +1049,10 @@ __global__ void __launch_bounds__(256) k_fix_accum_t(const FixArgs f) {
   }
   if (tid < f.d) f.partial[((size_t)slot * f.k + j) * f.d + tid] = acc;
   if (tid == 0) f.counts_out[(size_t)slot * f.k + j] = cnt;
+  if (tid == 0 && j == 0 && slot == 0 && f.st_w != nullptr && f.rstat != nullptr) {
+    f.st_w->fix_rows_cum = f.rstat[0];    // complete: the main kernel and k_fix_labels_t have finished
+    f.st_w->fix_cands_cum = f.rstat[1];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1239,6 +1244,7 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   f.partial = a.partials + (size_t)(plan.P - FIX_SLOTS) * k * d;
   f.counts_out = a.counts + (size_t)(plan.P - FIX_SLOTS) * k;
   f.st = st;
+  f.st_w = const_cast<B2kLoopState*>(st);
   k_fix_labels_t<<<plan.Pc - plan.grid, FIX_WARPS * 32, 0, s>>>(f);
   ctx->stats.kernel_launches++;
   if (do_update) {

@@ -20,6 +20,10 @@ struct B2kLoopState {
   double tol;
   double shift;              // last sum_j ||dc_j||^2
   double cost;               // last sum_i min_j ||x_i - c_j||^2 (w.r.t. the centers of that pass)
+  // large-shape kernel: deferred (exactly re-decided) rows / candidate distances evaluated, cumulative over the call
+  // (written by k_fix_accum_t; the host's convergence poll reads them to choose the path of the next burst)
+  unsigned long long fix_rows_cum;
+  unsigned long long fix_cands_cum;
 };
 
 // Layout of the reduced buffer R (doubles) that crosses NCCL: [k*d sums | k counts | 1 cost].
@@ -39,6 +43,9 @@ struct b2k_ctx {
   int grid_limit = 0;
   int probe = 0;                 // debug/experiment switch for the fused kernel (0 = normal)
   int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
+  int adaptive_path = 1;         // option "adaptive_path": a Lloyd loop on the large-shape kernel falls back to the generic
+                                 // kernels for its remaining iterations when most rows need the exact fix-up
+  int lloyd_switched = 0;        // the last lloyd_impl call did so (the fit's inertia pass follows it)
   int force_variant_t = 0;       // option "variant_t": route every supported shape through b2k_fused_t.cu (tests)
   int tma_box_rows = 0;          // option "tma_box_rows": rows per TMA box of b2k_debug_tma_stream (diagnostic; 0 = 128)
   int collect_recheck = 0;       // option "collect_recheck": fill stats.recheck_* (costs a stream sync per call)

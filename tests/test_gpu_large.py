@@ -166,3 +166,45 @@ def test_fit_large_inertia_and_estimator_path(ctx):
     assert out["n_iter_"] == ref["n_iter"]
     assert ko.max_center_rel_err(out["cluster_centers_"].cpu().numpy(), ref["centers"]) <= CENTER_RTOL
     assert abs(out["inertia_"] - ref["inertia"]) <= 1e-5 * ref["inertia"]
+
+
+def test_adaptive_path_leaves_the_screening_kernel_on_near_tie_data():
+    """A degenerate cloud (every row within 1e-3 of one point): every row is a near-tie between all clusters for 1xTF32
+    screening.  With kernel_path = auto the Lloyd loop measures the fix-up load of its first burst and runs the remaining
+    iterations on the generic kernels (b2k_stats.path_switch_iter).  Blobs never switch; uniform noise may or may not,
+    and stays within the parity tolerance of the oracle either way."""
+    from spark_rapids_ml_b200 import _native
+
+    n, d, k, iters = 40000, 256, 256, 12
+    rng = np.random.default_rng(5)
+    Xd = (1.0 + 1e-3 * rng.random((n, d))).astype(np.float32)
+    c = _native.Context(0)
+    try:
+        c.set_option("collect_recheck", 1)
+        res = {}
+        for adaptive in (1, 0):
+            c.set_option("adaptive_path", adaptive)
+            C = _dev(Xd[:k].copy())
+            n_it, _ = c.kmeans_lloyd(_dev(Xd), C, iters, -1.0)
+            st = c.stats()
+            Ch = C.cpu().numpy()
+            assert n_it == iters and np.isfinite(Ch).all() and Ch.min() >= Xd.min() - 1e-6 and Ch.max() <= Xd.max() + 1e-6
+            res[adaptive] = (st["path_switch_iter"], st["last_path"], st["recheck_rows"])
+        # default check_every = 4: the first burst's counters are read after the second burst is queued
+        assert res[1][0] == 8 and res[1][1] == 1
+        assert res[0][0] == -1 and res[0][1] == 2 and res[0][2] > res[1][2] > 0
+        c.set_option("adaptive_path", 1)
+        Xb, ctr = ko.make_blobs(20000, d, k, seed=3)
+        Cb = _dev((ctr + 0.25 * np.random.default_rng(0).normal(size=ctr.shape)).astype(np.float32))
+        c.kmeans_lloyd(_dev(Xb), Cb, iters, -1.0)
+        assert c.stats()["path_switch_iter"] == -1 and c.stats()["last_path"] == 2
+        Xu = ko.make_uniform(30000, d, seed=5)
+        C0 = Xu[:k].copy()
+        Cu = _dev(C0)
+        c.kmeans_lloyd(_dev(Xu), Cu, iters, -1.0)
+        lab0, _, margin0 = ko.assign(Xu, C0)
+        if margin0.min() > 1e-5:   # (an admissible tie row may send trajectories apart on uniform data)
+            ref = ko.lloyd([Xu], C0, iters, -1.0)
+            assert ko.max_center_rel_err(Cu.cpu().numpy(), ref["centers"]) <= 10 * CENTER_RTOL
+    finally:
+        c.close()

@@ -36,3 +36,17 @@ for name, XX, C in cases:
     for ev in prof.key_averages():
         if ev.device_time_total > 0:
             print("   %-60s n=%d avg=%.3f ms" % (ev.key[:60], ev.count, ev.device_time_total / ev.count / 1e3))
+if len(sys.argv) > 1 and sys.argv[1] == "uniform":   # the adaptive switch: 12 iterations on uniform noise, both settings
+    ctx.set_option("time_kernels", 1)
+    name, XX, C = cases[-1]
+    for adaptive in (1, 0, 1):
+        ctx.set_option("adaptive_path", adaptive)
+        Cc = C.clone(); ctx.kmeans_lloyd(XX, Cc, 12, -1.0)
+        st = ctx.stats()
+        print("uniform 12 iterations adaptive=%d: loop %.1f ms, switch at %d, last_path %d" % (adaptive, st["last_loop_ms"], st["path_switch_iter"], st["last_path"]))
+    ctx.set_option("kernel_path", 1)
+    Cc = C.clone(); ctx.kmeans_lloyd(XX, Cc, 12, -1.0)
+    print("uniform 12 iterations generic only: loop %.1f ms" % ctx.stats()["last_loop_ms"])
+    for nm, XX2, C2 in cases[:3]:
+        Cc = C2.clone(); ctx.kmeans_lloyd(XX2, Cc, 12, -1.0)
+        print(nm, "12 iterations generic only: loop %.1f ms" % ctx.stats()["last_loop_ms"])
