@@ -210,6 +210,59 @@ struct LoopBuffers {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// k > 256 on the large-shape kernel: the assignment runs as ceil(k / 256) screening + fix-up passes over chunks of
+// exactly 256 centres (the last chunk is [k - 256, k): the overlap is harmless for a min), each producing the exact
+// min distance sum (x - c)^2 and label of every row within its chunk; k_merge_chunk keeps the smaller distance
+// (strict '<': lowest cluster index on ties).  Replaces the SIMT assign of the generic path for d <= 256, d % 4 == 0
+// (the k-means|| candidate passes and Lloyd with k > 256); the update step stays the generic, label-driven one.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int CHUNK_K = 256;
+struct ChunkedAssign {
+  B2kFusedPlan plan;
+  void* ps = nullptr;        // plan scratch
+  int32_t* tmp_lab = nullptr;
+  float* tmp_md = nullptr;
+  int32_t* lab_acc = nullptr;   // used when the caller passes no labels / mindist buffer
+  float* md_acc = nullptr;
+};
+bool chunked_assign_ok(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
+  return k > CHUNK_K && ctx->kernel_path != B2K_PATH_GENERIC && n > 0 && b2k_fused_t_supported(ctx, n, d, CHUNK_K, X);
+}
+size_t chunked_assign_bytes(b2k_ctx* ctx, int64_t n, int d) {
+  B2kFusedPlan plan;
+  if (b2k_fused_t_plan(ctx, n, d, CHUNK_K, &plan) != B2K_OK) return 0;
+  return align_up(plan.scratch_bytes, 1024) + 4 * align_up((size_t)n * 4, 256) + 4096;
+}
+int chunked_assign_setup(b2k_ctx* ctx, int64_t n, int d, void* base, ChunkedAssign* ca) {
+  B2K_TRY(b2k_fused_t_plan(ctx, n, d, CHUNK_K, &ca->plan));
+  Arena A(base);
+  A.off = 0;
+  ca->tmp_lab = A.take<int32_t>(n);
+  ca->tmp_md = A.take<float>(n);
+  ca->lab_acc = A.take<int32_t>(n);
+  ca->md_acc = A.take<float>(n);
+  A.off = align_up(A.off, 1024);
+  ca->ps = A.base + A.off;
+  return B2K_OK;
+}
+// `base` must be 1 KB aligned scratch of chunked_assign_bytes(); b2k_fused_t_prepare(ca.plan, ca.ps, ...) done by the caller
+int chunked_assign_run(b2k_ctx* ctx, const ChunkedAssign& ca, const float* X, int64_t n, int d, const float* C, int k,
+                       int32_t* labels, float* mindist, const B2kLoopState* st, cudaStream_t s) {
+  int32_t* lab = labels ? labels : ca.lab_acc;
+  float* md = mindist ? mindist : ca.md_acc;
+  for (int c0 = 0; c0 < k; c0 += CHUNK_K) {
+    const int base = std::min(c0, k - CHUNK_K);
+    const bool first = c0 == 0;
+    B2K_TRY(b2k_launch_fused_t(ctx, ca.plan, ca.ps, X, n, d, C + (size_t)base * d, CHUNK_K, first ? lab : ca.tmp_lab,
+                               first ? md : ca.tmp_md, false, true, st, s, nullptr));
+    if (!first) B2K_TRY(b2k_launch_merge_chunk(ctx, md, lab, ca.tmp_md, ca.tmp_lab, base, n, st, s));
+  }
+  return B2K_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
 // Lloyd loop
 // ------------------------------------------------------------------------------------------------
 static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, float* C, int max_iter, double tol,
@@ -220,10 +273,12 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   auto since = [&](std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
-  int st_rc;
-  const bool fused = want_fused(ctx, n, d, k, X, &st_rc);
+  // k > 256 (d <= 256): the assignment runs in 256-centre chunks on the large-shape kernel, the update stays generic
+  const bool chunked = chunked_assign_ok(ctx, n, d, k, X);
+  int st_rc = B2K_OK;
+  const bool fused = chunked ? false : want_fused(ctx, n, d, k, X, &st_rc);
   B2K_TRY(st_rc);
-  ctx->stats.last_path = fused ? B2K_PATH_TCGEN05 : B2K_PATH_GENERIC;
+  ctx->stats.last_path = (fused || chunked) ? B2K_PATH_TCGEN05 : B2K_PATH_GENERIC;
 
   LoopBuffers B{};
   size_t gen_bytes = 0;
@@ -237,7 +292,8 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   const size_t rlen = b2k_reduced_len(k, d);
   size_t total = 4096 + align_up(rlen * 8, 256) + align_up((size_t)k * 8, 256) + align_up((size_t)k * 4, 256) +
                  (fused ? align_up(B.plan.scratch_bytes, 1024) + 2048 : 0) +
-                 (need_generic ? align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 4096 : 0);
+                 (need_generic ? align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 4096 : 0) +
+                 (chunked ? chunked_assign_bytes(ctx, n, d) + 2048 : 0);
   B2K_TRY(b2k_scratch_reserve(ctx, total));
   Arena A(ctx->scratch);
   B.st = A.take<B2kLoopState>(1);
@@ -252,6 +308,11 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   if (fused) {
     A.off = align_up(A.off, 1024);
     B.plan_scratch = A.base + A.off;
+  }
+  ChunkedAssign ca;
+  if (chunked) {
+    A.off = align_up(A.off, 1024);
+    B2K_TRY(chunked_assign_setup(ctx, n, d, A.base + A.off, &ca));
   }
 
   B2kLoopState init{};
@@ -282,6 +343,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
   B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
   if (fused && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, B.plan, B.plan_scratch, X, n, d, k, s));
+  if (chunked && max_iter > 0) B2K_TRY(b2k_fused_t_prepare(ctx, ca.plan, ca.ps, X, n, d, CHUNK_K, s));
   if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
   const double t_setup = since(t_entry);
   const auto t_loop = std::chrono::steady_clock::now();
@@ -315,8 +377,12 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
         B2K_TRY(b2k_launch_reduce_partials(ctx, partials, counts, cost_partials, B.plan.P, B.plan.Pc, k, d, B.R, B.st, s));
       } else {
         if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[0], s));
-        B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
-        B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, B.cnorm, k, B.labels, nullptr, B.st, s));
+        if (chunked) {
+          B2K_TRY(chunked_assign_run(ctx, ca, X, n, d, C, k, B.labels, nullptr, B.st, s));
+        } else {
+          B2K_TRY(b2k_launch_center_norms(ctx, C, k, d, B.cnorm, B.st, s));
+          B2K_TRY(b2k_launch_assign_generic(ctx, X, n, d, C, B.cnorm, k, B.labels, nullptr, B.st, s));
+        }
         B2K_TRY(b2k_launch_update_generic(ctx, X, n, d, B.labels, k, B.P, B.partials, B.counts, B.st, s));
         if (e) B2K_CUDA_OK(ctx, cudaEventRecord(e[1], s));
         B2K_TRY(b2k_launch_reduce_partials(ctx, B.partials, B.counts, nullptr, B.P, 0, k, d, B.R, B.st, s));
@@ -420,6 +486,29 @@ extern "C" int b2k_kmeans_lloyd(b2k_ctx* ctx, const float* X, int64_t n_local, i
 static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
                        float* mindist, double* cost_dev /* device, 1 double, may be NULL */, size_t scratch_off,
                        cudaStream_t s) {
+  if (chunked_assign_ok(ctx, n, d, k, X)) {   // k > 256: 256-centre chunks through the large-shape kernel
+    const int nblocks = 1024;
+    const size_t off = align_up(scratch_off, 1024);
+    size_t need = off + chunked_assign_bytes(ctx, n, d) + align_up((size_t)nblocks * 8, 256) + 1024;
+    if (need > ctx->scratch_bytes && scratch_off != 0)
+      return b2k_fail(ctx, B2K_ERR_STATE, "assign_impl: scratch must be pre-reserved by the caller");
+    B2K_TRY(b2k_scratch_reserve(ctx, need));
+    char* base = static_cast<char*>(ctx->scratch) + off;
+    ChunkedAssign ca;
+    B2K_TRY(chunked_assign_setup(ctx, n, d, base, &ca));
+    double* blocks = reinterpret_cast<double*>(base + chunked_assign_bytes(ctx, n, d));
+    B2K_TRY(b2k_fused_t_prepare(ctx, ca.plan, ca.ps, X, n, d, CHUNK_K, s));
+    B2K_TRY(chunked_assign_run(ctx, ca, X, n, d, C, k, labels, mindist, nullptr, s));
+    if (cost_dev) B2K_TRY(b2k_launch_sum_f32_to_f64(ctx, mindist ? mindist : ca.md_acc, n, cost_dev, blocks, nblocks, s));
+    ctx->stats.last_path = B2K_PATH_TCGEN05;
+    if (ctx->collect_recheck) {
+      unsigned long long rs[2];
+      B2K_TRY(b2k_fused_recheck_stats(ctx, ca.plan, ca.ps, n, CHUNK_K, d, rs, s));
+      ctx->stats.recheck_rows = (int64_t)rs[0];
+      ctx->stats.recheck_candidates = (int64_t)rs[1];
+    }
+    return B2K_OK;
+  }
   int st_rc;
   const bool fused = want_fused(ctx, n, d, k, X, &st_rc);
   B2K_TRY(st_rc);
@@ -473,6 +562,7 @@ static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const flo
 // upper bound of what assign_impl needs past scratch_off
 static size_t assign_scratch_bound(b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
   size_t b = align_up((size_t)k * 4, 256) + align_up((size_t)(n > 0 ? n : 1) * 4, 256) + 1024 * 8 + 4096;
+  if (chunked_assign_ok(ctx, n, d, k, X)) b = std::max(b, chunked_assign_bytes(ctx, n, d) + 1024 * 8 + 8192);
   if (b2k_fused_supported(ctx, n, d, k, X) && ctx->kernel_path != B2K_PATH_GENERIC) {
     B2kFusedPlan plan;
     if (b2k_fused_plan(ctx, n, d, k, &plan) == B2K_OK) b = std::max(b, align_up(plan.scratch_bytes, 1024) + 4096);
@@ -559,11 +649,12 @@ std::vector<int64_t> sample_distinct(std::mt19937_64& rng, int64_t total, int m)
   return chosen;
 }
 
-// Weighted greedy k-means++ followed by a few weighted Lloyd steps on the (small) candidate set — host side, on the
-// candidate-to-candidate squared distances D2 [M x M] computed on the device (every k-means++ centre IS a candidate, so
-// the greedy phase is table look-ups: k * trials * M instead of k * trials * M * d operations).
-void reduce_candidates(const std::vector<float>& P, const std::vector<float>& D2, const std::vector<double>& wts, int M, int d,
-                       int k, std::mt19937_64& rng, std::vector<float>* out) {
+// Weighted greedy k-means++ on the (small) candidate set — host side, on the candidate-to-candidate squared distances
+// D2 [M x M] computed on the device (every k-means++ centre IS a candidate, so the greedy phase is table look-ups:
+// k * trials * M instead of k * trials * M * d operations).  Returns the chosen candidate indices; the weighted Lloyd
+// refinement that follows runs on the device (init_kmeans_parallel).
+void reduce_candidates(const std::vector<float>& D2, const std::vector<double>& wts, int M, int k, std::mt19937_64& rng,
+                       std::vector<int64_t>* out) {
   std::vector<double> d2(M), nd2(M), bestd2(M);
   std::vector<int> chosen;
   chosen.reserve(k);
@@ -578,7 +669,7 @@ void reduce_candidates(const std::vector<float>& P, const std::vector<float>& D2
   for (int i = 0; i < M; ++i) { prob[i] = wts[i]; tot += prob[i]; }
   int first = pick(prob, tot);
   chosen.push_back(first);
-  for (int i = 0; i < M; ++i) d2[i] = (double)D2[(size_t)i * M + first];
+  for (int i = 0; i < M; ++i) d2[i] = (double)D2[(size_t)first * M + i];
   const int trials = 2 + (int)std::log((double)std::max(k, 2));
   for (int j = 1; j < k; ++j) {
     tot = 0;
@@ -588,48 +679,13 @@ void reduce_candidates(const std::vector<float>& P, const std::vector<float>& D2
     for (int tr = 0; tr < trials; ++tr) {
       int c = tot > 0 ? pick(prob, tot) : (int)(rng() % M);
       double pot = 0;
-      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], (double)D2[(size_t)i * M + c]); pot += wts[i] * nd2[i]; }
+      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], (double)D2[(size_t)c * M + i]); pot += wts[i] * nd2[i]; }
       if (best_pot < 0 || pot < best_pot) { best_pot = pot; best_c = c; bestd2 = nd2; }
     }
     chosen.push_back(best_c);
     d2 = bestd2;
   }
-  // weighted Lloyd refinement on the candidates (fp32 dot products, fp64 sums)
-  std::vector<float> C((size_t)k * d), cn(k);
-  for (int j = 0; j < k; ++j)
-    for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = P[(size_t)chosen[j] * d + t];
-  std::vector<int> lab(M);
-  std::vector<double> S((size_t)k * d), W(k);
-  for (int it = 0; it < 10; ++it) {
-    for (int j = 0; j < k; ++j) {
-      float s2 = 0.f;
-      for (int t = 0; t < d; ++t) s2 += C[(size_t)j * d + t] * C[(size_t)j * d + t];
-      cn[j] = s2;
-    }
-    for (int i = 0; i < M; ++i) {
-      const float* p = &P[(size_t)i * d];
-      float b = 3.4e38f;
-      int bj = 0;
-      for (int j = 0; j < k; ++j) {
-        const float* c = &C[(size_t)j * d];
-        float dot = 0.f;
-        for (int t = 0; t < d; ++t) dot += p[t] * c[t];
-        const float dist = cn[j] - 2.f * dot;
-        if (dist < b) { b = dist; bj = j; }
-      }
-      lab[i] = bj;
-    }
-    std::fill(S.begin(), S.end(), 0.0);
-    std::fill(W.begin(), W.end(), 0.0);
-    for (int i = 0; i < M; ++i) {
-      W[lab[i]] += wts[i];
-      for (int t = 0; t < d; ++t) S[(size_t)lab[i] * d + t] += wts[i] * (double)P[(size_t)i * d + t];
-    }
-    for (int j = 0; j < k; ++j)
-      if (W[j] > 0)
-        for (int t = 0; t < d; ++t) C[(size_t)j * d + t] = (float)(S[(size_t)j * d + t] / W[j]);
-  }
-  *out = C;
+  out->assign(chosen.begin(), chosen.end());
 }
 }  // namespace
 
@@ -762,21 +818,37 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
   B2K_CUDA_OK(ctx, cudaMemcpyAsync(wts.data(), hist, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
   for (auto& w : wts) w = std::max(w, 1e-12);
-  // candidate-to-candidate squared distances on the device (identical on every rank: same candidates, same kernel)
+  // candidate-to-candidate squared distances on the device (identical on every rank: same candidates, same kernel),
+  // greedy weighted k-means++ on the host (table look-ups), then 10 weighted Lloyd steps on the device: the assignment
+  // of the M candidates through the same kernels as any other assign pass, the weighted update in fixed order (fp64)
   std::vector<float> D2h((size_t)M * M);
-  {
-    B2K_TRY(b2k_scratch_reserve(ctx, fixed + abound + 4096 + (size_t)M * M * 4 + 1024));
-    // the scratch may have moved: only `cand` is needed from here on, and it was copied to P above
-    float* candd = reinterpret_cast<float*>(static_cast<char*>(ctx->scratch));
-    float* D2d = candd + (size_t)M * d;
-    B2K_CUDA_OK(ctx, cudaMemcpyAsync(candd, P.data(), P.size() * 4, cudaMemcpyHostToDevice, s));
-    B2K_TRY(b2k_launch_pairwise_sqdist(ctx, candd, M, d, D2d, s));
-    B2K_CUDA_OK(ctx, cudaMemcpyAsync(D2h.data(), D2d, D2h.size() * 4, cudaMemcpyDeviceToHost, s));
-    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  const size_t reg = align_up((size_t)M * d * 4, 256) + align_up((size_t)M * M * 4, 256) + align_up((size_t)M * 8, 256) +
+                     align_up((size_t)k * d * 4, 256) + align_up((size_t)M * 4, 256) + align_up((size_t)k * 8, 256) + 4096;
+  B2K_TRY(b2k_scratch_reserve(ctx, reg + assign_scratch_bound(ctx, M, d, k, static_cast<const float*>(ctx->scratch)) + 4096));
+  // the scratch may have moved: only `cand` is needed from here on, and it was copied to P above
+  Arena R(ctx->scratch);
+  float* candd = R.take<float>((size_t)M * d);
+  float* D2d = R.take<float>((size_t)M * M);
+  double* wts_dev = R.take<double>(M);
+  float* Ck_dev = R.take<float>((size_t)k * d);
+  int32_t* lab_dev = R.take<int32_t>(M);
+  int64_t* chosen_dev = R.take<int64_t>(k);
+  const size_t refine_off = align_up(R.off, 1024);
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(candd, P.data(), P.size() * 4, cudaMemcpyHostToDevice, s));
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(wts_dev, wts.data(), (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  B2K_TRY(b2k_launch_pairwise_sqdist(ctx, candd, M, d, D2d, s));
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(D2h.data(), D2d, D2h.size() * 4, cudaMemcpyDeviceToHost, s));
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  std::vector<int64_t> chosen;
+  reduce_candidates(D2h, wts, M, k, rng, &chosen);  // same seed + same inputs => identical on every rank
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(chosen_dev, chosen.data(), (size_t)k * 8, cudaMemcpyHostToDevice, s));
+  B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `chosen` is pageable
+  B2K_TRY(b2k_launch_gather_rows(ctx, candd, d, chosen_dev, k, Ck_dev, 0, s));
+  for (int it = 0; it < 10; ++it) {
+    B2K_TRY(assign_impl(ctx, candd, M, d, Ck_dev, k, lab_dev, nullptr, nullptr, refine_off, s));
+    B2K_TRY(b2k_launch_weighted_update(ctx, candd, wts_dev, lab_dev, M, d, k, Ck_dev, s));
   }
-  std::vector<float> Ck;
-  reduce_candidates(P, D2h, wts, M, d, k, rng, &Ck);  // same seed + same inputs => identical on every rank
-  B2K_CUDA_OK(ctx, cudaMemcpyAsync(C, Ck.data(), Ck.size() * 4, cudaMemcpyHostToDevice, s));
+  B2K_CUDA_OK(ctx, cudaMemcpyAsync(C, Ck_dev, (size_t)k * d * 4, cudaMemcpyDeviceToDevice, s));
   B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
   return B2K_OK;
 }

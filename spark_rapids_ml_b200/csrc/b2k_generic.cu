@@ -477,6 +477,58 @@ int b2k_launch_min_inplace(b2k_ctx* ctx, float* a, const float* b, int64_t n, cu
   return B2K_OK;
 }
 
+// chunked assign (k > 256): fold one chunk's (min distance, local label) into the running (min distance, global label);
+// strict '<' keeps the earlier chunk (= the lower cluster index) on ties
+__global__ void k_merge_chunk(float* __restrict__ md_acc, int32_t* __restrict__ lab_acc, const float* __restrict__ md,
+                              const int32_t* __restrict__ lab, int base, int64_t n, const B2kLoopState* st) {
+  B2K_EARLY_EXIT(st);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = md[i];
+    if (v < md_acc[i]) {
+      md_acc[i] = v;
+      lab_acc[i] = lab[i] + base;
+    }
+  }
+}
+int b2k_launch_merge_chunk(b2k_ctx* ctx, float* md_acc, int32_t* lab_acc, const float* md, const int32_t* lab, int base,
+                           int64_t n, const B2kLoopState* st, cudaStream_t s) {
+  if (n <= 0) return B2K_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  k_merge_chunk<<<(unsigned)blocks, 256, 0, s>>>(md_acc, lab_acc, md, lab, base, n, st);
+  ctx->stats.kernel_launches++;
+  B2K_CUDA_OK(ctx, cudaGetLastError());
+  return B2K_OK;
+}
+
+// weighted centroid update of the k-means|| candidate refinement: one CTA per centre scans the (few thousand) candidates
+// in index order — fp64 sums, fixed order, identical on every rank
+__global__ void __launch_bounds__(256) k_weighted_update(const float* __restrict__ P, const double* __restrict__ w,
+                                                         const int32_t* __restrict__ lab, int M, int d,
+                                                         float* __restrict__ C) {
+  const int j = (int)blockIdx.x;
+  for (int t = (int)threadIdx.x; t < d; t += (int)blockDim.x) {
+    double S = 0.0, W = 0.0;
+    for (int i = 0; i < M; ++i) {
+      if (lab[i] == j) {
+        const double wi = w[i];
+        S += wi * (double)P[(size_t)i * d + t];
+        W += wi;
+      }
+    }
+    if (W > 0.0) C[(size_t)j * d + t] = (float)(S / W);
+  }
+}
+int b2k_launch_weighted_update(b2k_ctx* ctx, const float* P, const double* w, const int32_t* lab, int M, int d, int k,
+                               float* C, cudaStream_t s) {
+  k_weighted_update<<<k, 256, 0, s>>>(P, w, lab, M, d, C);
+  ctx->stats.kernel_launches++;
+  B2K_CUDA_OK(ctx, cudaGetLastError());
+  return B2K_OK;
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

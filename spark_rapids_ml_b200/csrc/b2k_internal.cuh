@@ -132,6 +132,8 @@ int b2k_launch_bernoulli_pick(b2k_ctx* ctx, const float* mind, int64_t n, int64_
                               int* n_picked, int cap, cudaStream_t s);
 int b2k_launch_histogram(b2k_ctx* ctx, const int32_t* labels, int64_t n, int m, double* hist,
                          cudaStream_t s);
+int b2k_launch_weighted_update(b2k_ctx* ctx, const float* P, const double* w, const int32_t* lab, int M, int d, int k,
+                               float* C, cudaStream_t s);
 int b2k_launch_pairwise_sqdist(b2k_ctx* ctx, const float* P, int M, int d, float* D2, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +175,8 @@ int b2k_fused_t_prepare(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scrat
 int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d,
                        const float* C, int k, int32_t* labels_out, float* mindist_out, bool do_update, bool need_cost,
                        const B2kLoopState* st, cudaStream_t s, const double* prev_counts);
+int b2k_launch_merge_chunk(b2k_ctx* ctx, float* md_acc, int32_t* lab_acc, const float* md, const int32_t* lab, int base,
+                           int64_t n, const B2kLoopState* st, cudaStream_t s);
 int b2k_fused_encode_2d(b2k_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int l2_256);
 

@@ -208,3 +208,49 @@ def test_adaptive_path_leaves_the_screening_kernel_on_near_tie_data():
             assert ko.max_center_rel_err(Cu.cpu().numpy(), ref["centers"]) <= 10 * CENTER_RTOL
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("n,d,k,gen", [
+    (6000, 256, 600, "blobs"),      # 3 chunks, the last one overlapping the second ([344, 600))
+    (5000, 64, 257, "uniform"),     # the smallest chunked k; DP = 128 instantiation
+    (3000, 128, 1024, "blobs"),
+])
+def test_assign_and_lloyd_beyond_256_clusters_run_in_chunks(n, d, k, gen):
+    """k > 256 (d <= 256): the assignment runs as 256-centre chunks of the large-shape kernel merged by exact min
+    distance; Lloyd keeps the generic label-driven update.  Same parity rule as every other path."""
+    from spark_rapids_ml_b200 import _native
+
+    X = ko.make_blobs(n, d, k, seed=9)[0] if gen == "blobs" else ko.make_uniform(n, d, seed=9)
+    rng = np.random.default_rng(4)
+    C0 = X[rng.choice(n, size=k, replace=False)].copy()
+    c = _native.Context(0)
+    try:
+        before = c.stats()["fused_tc_launches"]
+        labels, md = c.kmeans_assign(_dev(X), _dev(C0), want_mindist=True)
+        st = c.stats()
+        assert st["last_path"] == 2 and st["fused_tc_launches"] - before == -(-k // 256)
+        cmp = ko.compare_labels(X, C0, labels.cpu().numpy(), tau=TAU)
+        assert cmp["n_mismatch_outside_margin"] == 0, cmp
+        _, md_o, _ = ko.assign(X, C0)
+        xn = (X.astype(np.float64) ** 2).sum(1)
+        np.testing.assert_allclose(md.cpu().numpy(), md_o, rtol=2e-4, atol=2e-5 * float(xn.max()) + 1e-6)
+        # Lloyd: one exact step, and a few iterations on blobs
+        C1, _, _ = ko.lloyd_iteration([X], C0)
+        one = _dev(C0)
+        c.kmeans_lloyd(_dev(X), one, 1, -1.0)
+        lab0, _, margin0 = ko.assign(X, C0)
+        if margin0.min() > 1e-5:
+            assert ko.max_center_rel_err(one.cpu().numpy(), C1) <= CENTER_RTOL
+        if gen == "blobs":
+            ref = ko.lloyd([X], C0, 3, -1.0)
+            C = _dev(C0)
+            n_it, _ = c.kmeans_lloyd(_dev(X), C, 3, -1.0)
+            assert n_it == 3 and c.stats()["last_path"] == 2
+            assert ko.max_center_rel_err(C.cpu().numpy(), ref["centers"]) <= CENTER_RTOL
+        # the generic path still exists and agrees
+        c.set_option("kernel_path", 1)
+        lg, _ = c.kmeans_assign(_dev(X), _dev(C0))
+        assert c.stats()["last_path"] == 1
+        assert ko.compare_labels(X, C0, lg.cpu().numpy(), tau=TAU)["n_mismatch_outside_margin"] == 0
+    finally:
+        c.close()
