@@ -210,34 +210,43 @@ struct LoopBuffers {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// k > 256 on the large-shape kernel: the assignment runs as ceil(k / 256) screening + fix-up passes over chunks of
-// exactly 256 centres (the last chunk is [k - 256, k): the overlap is harmless for a min), each producing the exact
-// min distance sum (x - c)^2 and label of every row within its chunk; k_merge_chunk keeps the smaller distance
-// (strict '<': lowest cluster index on ties).  Replaces the SIMT assign of the generic path for d <= 256, d % 4 == 0
-// (the k-means|| candidate passes and Lloyd with k > 256); the update step stays the generic, label-driven one.
+// Chunked assignment for cluster counts beyond one fused pass: the centres are cut into chunks of exactly CH (the last
+// chunk is [k - CH, k): the overlap is harmless for a min), each chunk runs one fused assign pass that yields the min
+// distance and label of every row within the chunk, and k_merge_chunk keeps the smaller distance (strict '<': lowest
+// cluster index on ties).  d <= 128: CH = 128 through the 3xTF32 kernel (exact, no fix-up); 128 < d <= 256: CH = 256
+// through the large-shape kernel (1xTF32 screening + exact fix-up).  Used for k > 256 (assign passes, and Lloyd with the
+// generic label-driven update) and — d <= 128 only — for k > 128 when the caller expects near-ties (the k-means||
+// candidate passes: candidates drawn from one blob are almost equidistant from its rows, which is the worst case of
+// the screening kernel and free for the 3xTF32 one).  Replaces the SIMT assign of the generic path for d % 4 == 0.
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int CHUNK_K = 256;
 struct ChunkedAssign {
   B2kFusedPlan plan;
+  int ch = 0;                // chunk size
   void* ps = nullptr;        // plan scratch
   int32_t* tmp_lab = nullptr;
   float* tmp_md = nullptr;
   int32_t* lab_acc = nullptr;   // used when the caller passes no labels / mindist buffer
   float* md_acc = nullptr;
 };
-bool chunked_assign_ok(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
-  return k > CHUNK_K && ctx->kernel_path != B2K_PATH_GENERIC && n > 0 && b2k_fused_t_supported(ctx, n, d, CHUNK_K, X);
+// chunk size, 0 = this (d, k) is not chunked
+int chunked_assign_ch(const b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
+  if (ctx->kernel_path == B2K_PATH_GENERIC || n <= 0 || d > 256) return 0;
+  const int ch = (d <= 128 && !ctx->force_variant_t) ? 128 : 256;
+  const bool want = k > 256 || (ch == 128 && k > 128 && ctx->near_tie_hint);
+  if (!want || !b2k_fused_supported(ctx, n, d, ch, X)) return 0;
+  return ch;
 }
-size_t chunked_assign_bytes(b2k_ctx* ctx, int64_t n, int d) {
+size_t chunked_assign_bytes(b2k_ctx* ctx, int64_t n, int d, int ch) {
   B2kFusedPlan plan;
-  if (b2k_fused_t_plan(ctx, n, d, CHUNK_K, &plan) != B2K_OK) return 0;
+  if (b2k_fused_plan(ctx, n, d, ch, &plan) != B2K_OK) return 0;
   return align_up(plan.scratch_bytes, 1024) + 4 * align_up((size_t)n * 4, 256) + 4096;
 }
-int chunked_assign_setup(b2k_ctx* ctx, int64_t n, int d, void* base, ChunkedAssign* ca) {
-  B2K_TRY(b2k_fused_t_plan(ctx, n, d, CHUNK_K, &ca->plan));
+// `base`: 1 KB aligned scratch of chunked_assign_bytes(); the caller runs b2k_fused_prepare(ca.plan, ca.ps, ..., ca.ch)
+int chunked_assign_setup(b2k_ctx* ctx, int64_t n, int d, int ch, void* base, ChunkedAssign* ca) {
+  ca->ch = ch;
+  B2K_TRY(b2k_fused_plan(ctx, n, d, ch, &ca->plan));
   Arena A(base);
-  A.off = 0;
   ca->tmp_lab = A.take<int32_t>(n);
   ca->tmp_md = A.take<float>(n);
   ca->lab_acc = A.take<int32_t>(n);
@@ -246,16 +255,15 @@ int chunked_assign_setup(b2k_ctx* ctx, int64_t n, int d, void* base, ChunkedAssi
   ca->ps = A.base + A.off;
   return B2K_OK;
 }
-// `base` must be 1 KB aligned scratch of chunked_assign_bytes(); b2k_fused_t_prepare(ca.plan, ca.ps, ...) done by the caller
 int chunked_assign_run(b2k_ctx* ctx, const ChunkedAssign& ca, const float* X, int64_t n, int d, const float* C, int k,
                        int32_t* labels, float* mindist, const B2kLoopState* st, cudaStream_t s) {
   int32_t* lab = labels ? labels : ca.lab_acc;
   float* md = mindist ? mindist : ca.md_acc;
-  for (int c0 = 0; c0 < k; c0 += CHUNK_K) {
-    const int base = std::min(c0, k - CHUNK_K);
+  for (int c0 = 0; c0 < k; c0 += ca.ch) {
+    const int base = std::min(c0, k - ca.ch);
     const bool first = c0 == 0;
-    B2K_TRY(b2k_launch_fused_t(ctx, ca.plan, ca.ps, X, n, d, C + (size_t)base * d, CHUNK_K, first ? lab : ca.tmp_lab,
-                               first ? md : ca.tmp_md, false, true, st, s, nullptr));
+    B2K_TRY(b2k_launch_fused(ctx, ca.plan, ca.ps, X, n, d, C + (size_t)base * d, ca.ch, first ? lab : ca.tmp_lab,
+                             first ? md : ca.tmp_md, false, st, s));
     if (!first) B2K_TRY(b2k_launch_merge_chunk(ctx, md, lab, ca.tmp_md, ca.tmp_lab, base, n, st, s));
   }
   return B2K_OK;
@@ -274,7 +282,8 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
   // k > 256 (d <= 256): the assignment runs in 256-centre chunks on the large-shape kernel, the update stays generic
-  const bool chunked = chunked_assign_ok(ctx, n, d, k, X);
+  const int chunk_ch = k > 256 ? chunked_assign_ch(ctx, n, d, k, X) : 0;
+  const bool chunked = chunk_ch != 0;
   int st_rc = B2K_OK;
   const bool fused = chunked ? false : want_fused(ctx, n, d, k, X, &st_rc);
   B2K_TRY(st_rc);
@@ -293,7 +302,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   size_t total = 4096 + align_up(rlen * 8, 256) + align_up((size_t)k * 8, 256) + align_up((size_t)k * 4, 256) +
                  (fused ? align_up(B.plan.scratch_bytes, 1024) + 2048 : 0) +
                  (need_generic ? align_up((size_t)n * 4, 256) + align_up(gen_bytes, 256) + 4096 : 0) +
-                 (chunked ? chunked_assign_bytes(ctx, n, d) + 2048 : 0);
+                 (chunked ? chunked_assign_bytes(ctx, n, d, chunk_ch) + 2048 : 0);
   B2K_TRY(b2k_scratch_reserve(ctx, total));
   Arena A(ctx->scratch);
   B.st = A.take<B2kLoopState>(1);
@@ -312,7 +321,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   ChunkedAssign ca;
   if (chunked) {
     A.off = align_up(A.off, 1024);
-    B2K_TRY(chunked_assign_setup(ctx, n, d, A.base + A.off, &ca));
+    B2K_TRY(chunked_assign_setup(ctx, n, d, chunk_ch, A.base + A.off, &ca));
   }
 
   B2kLoopState init{};
@@ -343,7 +352,7 @@ static int lloyd_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, flo
   B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
   B2K_CUDA_OK(ctx, cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
   if (fused && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, B.plan, B.plan_scratch, X, n, d, k, s));
-  if (chunked && max_iter > 0) B2K_TRY(b2k_fused_t_prepare(ctx, ca.plan, ca.ps, X, n, d, CHUNK_K, s));
+  if (chunked && max_iter > 0) B2K_TRY(b2k_fused_prepare(ctx, ca.plan, ca.ps, X, n, d, chunk_ch, s));
   if (ctx->time_kernels) B2K_CUDA_OK(ctx, cudaEventRecord(loop0, s));
   const double t_setup = since(t_entry);
   const auto t_loop = std::chrono::steady_clock::now();
@@ -486,24 +495,25 @@ extern "C" int b2k_kmeans_lloyd(b2k_ctx* ctx, const float* X, int64_t n_local, i
 static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
                        float* mindist, double* cost_dev /* device, 1 double, may be NULL */, size_t scratch_off,
                        cudaStream_t s) {
-  if (chunked_assign_ok(ctx, n, d, k, X)) {   // k > 256: 256-centre chunks through the large-shape kernel
+  if (const int ch = chunked_assign_ch(ctx, n, d, k, X)) {   // chunks of ch centres through a fused assign pass each
     const int nblocks = 1024;
     const size_t off = align_up(scratch_off, 1024);
-    size_t need = off + chunked_assign_bytes(ctx, n, d) + align_up((size_t)nblocks * 8, 256) + 1024;
+    const size_t cbytes = chunked_assign_bytes(ctx, n, d, ch);
+    size_t need = off + cbytes + align_up((size_t)nblocks * 8, 256) + 1024;
     if (need > ctx->scratch_bytes && scratch_off != 0)
       return b2k_fail(ctx, B2K_ERR_STATE, "assign_impl: scratch must be pre-reserved by the caller");
     B2K_TRY(b2k_scratch_reserve(ctx, need));
     char* base = static_cast<char*>(ctx->scratch) + off;
     ChunkedAssign ca;
-    B2K_TRY(chunked_assign_setup(ctx, n, d, base, &ca));
-    double* blocks = reinterpret_cast<double*>(base + chunked_assign_bytes(ctx, n, d));
-    B2K_TRY(b2k_fused_t_prepare(ctx, ca.plan, ca.ps, X, n, d, CHUNK_K, s));
+    B2K_TRY(chunked_assign_setup(ctx, n, d, ch, base, &ca));
+    double* blocks = reinterpret_cast<double*>(base + cbytes);
+    B2K_TRY(b2k_fused_prepare(ctx, ca.plan, ca.ps, X, n, d, ch, s));
     B2K_TRY(chunked_assign_run(ctx, ca, X, n, d, C, k, labels, mindist, nullptr, s));
     if (cost_dev) B2K_TRY(b2k_launch_sum_f32_to_f64(ctx, mindist ? mindist : ca.md_acc, n, cost_dev, blocks, nblocks, s));
     ctx->stats.last_path = B2K_PATH_TCGEN05;
     if (ctx->collect_recheck) {
       unsigned long long rs[2];
-      B2K_TRY(b2k_fused_recheck_stats(ctx, ca.plan, ca.ps, n, CHUNK_K, d, rs, s));
+      B2K_TRY(b2k_fused_recheck_stats(ctx, ca.plan, ca.ps, n, ch, d, rs, s));
       ctx->stats.recheck_rows = (int64_t)rs[0];
       ctx->stats.recheck_candidates = (int64_t)rs[1];
     }
@@ -562,7 +572,7 @@ static int assign_impl(b2k_ctx* ctx, const float* X, int64_t n, int d, const flo
 // upper bound of what assign_impl needs past scratch_off
 static size_t assign_scratch_bound(b2k_ctx* ctx, int64_t n, int d, int k, const float* X) {
   size_t b = align_up((size_t)k * 4, 256) + align_up((size_t)(n > 0 ? n : 1) * 4, 256) + 1024 * 8 + 4096;
-  if (chunked_assign_ok(ctx, n, d, k, X)) b = std::max(b, chunked_assign_bytes(ctx, n, d) + 1024 * 8 + 8192);
+  if (const int ch = chunked_assign_ch(ctx, n, d, k, X)) b = std::max(b, chunked_assign_bytes(ctx, n, d, ch) + 1024 * 8 + 8192);
   if (b2k_fused_supported(ctx, n, d, k, X) && ctx->kernel_path != B2K_PATH_GENERIC) {
     B2kFusedPlan plan;
     if (b2k_fused_plan(ctx, n, d, k, &plan) == B2K_OK) b = std::max(b, align_up(plan.scratch_bytes, 1024) + 4096);
@@ -706,6 +716,11 @@ static int init_random(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, ui
 // (clustering.py:134-136).  Distributional parity only (the reference's own seeded test is xfail).
 static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, uint64_t seed,
                                 double oversampling, float* C, cudaStream_t s) {
+  struct HintGuard {   // the candidate passes are near-tie heavy: see chunked_assign_ch
+    b2k_ctx* c;
+    explicit HintGuard(b2k_ctx* c_) : c(c_) { c->near_tie_hint = 1; }
+    ~HintGuard() { c->near_tie_hint = 0; }
+  } hint_guard(ctx);
   const int rounds = 5;
   Rows rows;
   B2K_TRY(gather_sizes(ctx, n, &rows, s));

@@ -45,7 +45,8 @@ struct b2k_ctx {
   int pair = 1;                  // option "pair": use the cta_group::2 instantiation where available (default on)
   int adaptive_path = 1;         // option "adaptive_path": a Lloyd loop on the large-shape kernel falls back to the generic
                                  // kernels for its remaining iterations when most rows need the exact fix-up
-  int lloyd_switched = 0;        // the last lloyd_impl call did so (the fit's inertia pass follows it)
+  int lloyd_switched = 0;
+  int near_tie_hint = 0;         // set around the k-means|| candidate passes: prefer exact 128-centre chunks (d <= 128)        // the last lloyd_impl call did so (the fit's inertia pass follows it)
   int force_variant_t = 0;       // option "variant_t": route every supported shape through b2k_fused_t.cu (tests)
   int tma_box_rows = 0;          // option "tma_box_rows": rows per TMA box of b2k_debug_tma_stream (diagnostic; 0 = 128)
   int collect_recheck = 0;       // option "collect_recheck": fill stats.recheck_* (costs a stream sync per call)

@@ -216,8 +216,8 @@ def test_adaptive_path_leaves_the_screening_kernel_on_near_tie_data():
     (3000, 128, 1024, "blobs"),
 ])
 def test_assign_and_lloyd_beyond_256_clusters_run_in_chunks(n, d, k, gen):
-    """k > 256 (d <= 256): the assignment runs as 256-centre chunks of the large-shape kernel merged by exact min
-    distance; Lloyd keeps the generic label-driven update.  Same parity rule as every other path."""
+    """k > 256 (d <= 256): the assignment runs as chunks of 128 (d <= 128, 3xTF32 kernel) or 256 centres (large-shape
+    kernel) merged by min distance; Lloyd keeps the generic label-driven update.  Same parity rule as every other path."""
     from spark_rapids_ml_b200 import _native
 
     X = ko.make_blobs(n, d, k, seed=9)[0] if gen == "blobs" else ko.make_uniform(n, d, seed=9)
@@ -228,7 +228,8 @@ def test_assign_and_lloyd_beyond_256_clusters_run_in_chunks(n, d, k, gen):
         before = c.stats()["fused_tc_launches"]
         labels, md = c.kmeans_assign(_dev(X), _dev(C0), want_mindist=True)
         st = c.stats()
-        assert st["last_path"] == 2 and st["fused_tc_launches"] - before == -(-k // 256)
+        ch = 128 if d <= 128 else 256     # d <= 128: exact 3xTF32 chunks; else the large-shape kernel
+        assert st["last_path"] == 2 and st["fused_tc_launches"] - before == -(-k // ch)
         cmp = ko.compare_labels(X, C0, labels.cpu().numpy(), tau=TAU)
         assert cmp["n_mismatch_outside_margin"] == 0, cmp
         _, md_o, _ = ko.assign(X, C0)

@@ -2,7 +2,7 @@ import sys, time, torch
 sys.path.insert(0, ".")
 from spark_rapids_ml_b200 import _native
 ctx = _native.Context(0)
-for (n, d, k) in ((2_000_000, 256, 256), (2_000_000, 128, 1024), (12_500_000, 256, 256)):
+for (n, d, k) in ((2_000_000, 256, 256), (2_000_000, 128, 1024), (12_500_000, 256, 256), (10_000_000, 128, 64)):
     g = torch.Generator(device="cuda").manual_seed(1)
     ctr = torch.rand((k, d), generator=g, device="cuda") * 20 - 10
     X = (ctr[torch.randint(0, k, (n,), generator=g, device="cuda")] + torch.randn((n, d), generator=g, device="cuda")).contiguous()
