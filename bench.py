@@ -619,6 +619,17 @@ def main():
                                "b2k_ingest_append per batch -> device concat -> b2k_kmeans_fit -> model rows; "
                                "wall clock, best of 2 (tol ~ 0: all %d iterations run)"
                                % (k, args.e2e_iters, (n_local + 9999) // 10000, args.e2e_iters)}
+                # the same fit with the estimator's DEFAULT initMode (k-means||, clustering.py:86-98): the initialiser's
+                # candidate passes are part of what a default user call pays
+                est2 = KMeans(k=k, maxIter=args.e2e_iters, tol=1e-30, seed=1, num_workers=1)
+                est2.setFeaturesCol("features")
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                model = est2.fit(df)
+                torch.cuda.synchronize(dev)
+                dt2 = time.perf_counter() - t0
+                e2e["default_init_kmeans_parallel"] = {"value": n_total * args.e2e_iters / dt2, "unit": UNIT,
+                                                       "ms_per_fit": dt2 * 1e3}
                 del df, model
             else:
                 e2e = dict(e2e_cabi)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 cfg = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
 SPEC = {"cfg2": dict(rep="fused_full.ncu-rep", kernel="k_fused_assign_update<64,128,PAIR,0> (3xTF32)", n=10_000_000, d=128, k=64),
-        "cfg3": dict(rep="fused_t_full.ncu-rep", kernel="k_fused_t<8,true> (1xTF32 screening + exact recheck)", n=12_500_000, d=256, k=256)}[cfg]
+        "cfg3": dict(rep="fused_t_full.ncu-rep", kernel="k_fused_t<8,true> (1xTF32 screening; near-tie rows deferred to k_fix_labels_t / k_fix_accum_t)", n=12_500_000, d=256, k=256)}[cfg]
 rep = os.path.join(ROOT, "gpurun_out", SPEC["rep"])
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
