@@ -305,25 +305,52 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
             raise ValueError("a Spark Param without GPU support is set and spark_rapids_ml_b200 has no CPU fallback")
         return self._fit_internal(dataset, None)[0]
 
-    # -- persistence (core.py:268-307) --
+    # -- persistence (core.py:268-307): Spark's DefaultParamsWriter layout (path/metadata/part-00000 JSON) --
     def save(self, path: str, overwrite: bool = True) -> None:
-        _save_metadata(self, path, overwrite)
+        w = self.write()
+        (w.overwrite() if overwrite else w).save(path)
 
-    def write(self) -> "_Writer":
-        return _Writer(self)
+    def write(self) -> Any:
+        if _spark_context_active():   # real pyspark with a live SparkContext: MLWriter + DefaultParamsWriter
+            from . import spark_binding
+
+            return spark_binding.make_writer(self, None)
+        return _Writer(self, None)
+
+    @classmethod
+    def read(cls) -> Any:
+        if _spark_context_active():
+            from . import spark_binding
+
+            return spark_binding.make_reader(cls, False)
+        return _Reader(cls, False)
 
     @classmethod
     def load(cls, path: str) -> "_CumlEstimator":
-        meta = _load_metadata(path)
-        inst = cls()
-        inst.uid = meta["uid"]
-        _set_params_from_metadata(inst, meta)
-        return inst
+        return cls.read().load(path)
 
 
+def _spark_context_active() -> bool:
+    if not HAVE_PYSPARK:
+        return False
+    try:
+        from pyspark import SparkContext
+
+        return SparkContext._active_spark_context is not None
+    except Exception:
+        return False
+
+
+# Local-filesystem writer / reader producing and accepting the SAME directory layout as pyspark's DefaultParamsWriter and
+# the reference's _CumlEstimatorWriter / _CumlModelWriter (core.py:268-355): path/metadata/part-00000 holds one JSON
+# object {class, timestamp, sparkVersion, uid, paramMap, defaultParamMap, _cuml_params, _num_workers, _float32_inputs};
+# a model adds path/data/part-00000 = json.dumps(model attributes); Hadoop-style _SUCCESS markers beside both.  A
+# directory written by the reference therefore loads here and vice versa (class names are not compared, as in the
+# reference's readers, which call DefaultParamsReader.loadMetadata without an expected class).
 class _Writer:
-    def __init__(self, inst: Any):
+    def __init__(self, inst: Any, model_attributes: Optional[Dict[str, Any]]):
         self.inst = inst
+        self.model_attributes = model_attributes
         self._overwrite = False
 
     def overwrite(self) -> "_Writer":
@@ -331,15 +358,73 @@ class _Writer:
         return self
 
     def save(self, path: str) -> None:
-        self.inst.save(path, overwrite=self._overwrite)
+        _save_metadata(self.inst, path, self._overwrite)
+        if self.model_attributes is not None:
+            _write_part(os.path.join(path, "data"), json.dumps(self.model_attributes))
+
+
+class _Reader:
+    def __init__(self, cls: Any, is_model: bool):
+        self.cls = cls
+        self.is_model = is_model
+
+    def load(self, path: str) -> Any:
+        meta = _load_metadata(path)
+        if self.is_model:
+            inst = self.cls(**json.loads(_read_part(os.path.join(path, "data"))))
+        else:
+            inst = self.cls()
+        _reset_uid(inst, meta["uid"])
+        _set_params_from_metadata(inst, meta)
+        return inst
+
+
+def _reset_uid(inst: Any, uid: str) -> None:
+    if hasattr(inst, "_resetUid"):   # pyspark Params: re-parents the Param objects as well
+        inst._resetUid(uid)
+    else:
+        inst.uid = uid
+
+
+def _write_part(dirname: str, text: str) -> None:
+    os.makedirs(dirname, exist_ok=True)
+    with open(os.path.join(dirname, "part-00000"), "w") as f:
+        f.write(text + "\n")
+    open(os.path.join(dirname, "_SUCCESS"), "w").close()
+
+
+def _read_part(dirname: str) -> str:
+    parts = sorted(f for f in os.listdir(dirname) if f.startswith("part-"))
+    if not parts:
+        raise IOError(f"no part file under {dirname}")
+    for name in parts:   # saveAsTextFile of a one-element RDD may leave empty parts beside the one that has the line
+        with open(os.path.join(dirname, name)) as f:
+            text = f.read().strip()
+        if text:
+            return text.splitlines()[0]
+    raise IOError(f"empty part files under {dirname}")
+
+
+def _spark_version() -> str:
+    if HAVE_PYSPARK:
+        try:
+            import pyspark
+
+            return str(pyspark.__version__)
+        except Exception:
+            pass
+    return "3.5.0"   # what DefaultParamsReader parses with majorMinorVersion(); no Spark is involved in a local save
 
 
 def _save_metadata(inst: Any, path: str, overwrite: bool, extra: Optional[Dict[str, Any]] = None) -> None:
+    import time
+
     if os.path.exists(path) and not overwrite:
         raise IOError(f"Path {path} already exists. To overwrite it, use write().overwrite().save(path).")
-    os.makedirs(os.path.join(path, "metadata"), exist_ok=True)
     meta = {
         "class": inst.__module__ + "." + inst.__class__.__name__,
+        "timestamp": int(time.time() * 1000),
+        "sparkVersion": _spark_version(),
         "uid": inst.uid,
         "paramMap": {p.name: v for p, v in inst._paramMap.items()},
         "defaultParamMap": {p.name: v for p, v in inst._defaultParamMap.items()},
@@ -349,13 +434,11 @@ def _save_metadata(inst: Any, path: str, overwrite: bool, extra: Optional[Dict[s
     }
     if extra:
         meta.update(extra)
-    with open(os.path.join(path, "metadata", "part-00000"), "w") as f:
-        f.write(json.dumps(meta))
+    _write_part(os.path.join(path, "metadata"), json.dumps(meta, separators=(",", ":")))
 
 
 def _load_metadata(path: str) -> Dict[str, Any]:
-    with open(os.path.join(path, "metadata", "part-00000")) as f:
-        return json.loads(f.read())
+    return json.loads(_read_part(os.path.join(path, "metadata")))
 
 
 def _set_params_from_metadata(inst: Any, meta: Dict[str, Any]) -> None:
@@ -393,25 +476,29 @@ class _CumlModel(ModelBase, _CumlParams, _CumlCommon):
     def _out_schema(self, input_schema: Any) -> Any:
         raise NotImplementedError
 
-    # -- persistence (core.py:310-355) --
+    # -- persistence (core.py:310-355): metadata as the estimator + path/data = json.dumps(model attributes) --
     def save(self, path: str, overwrite: bool = True) -> None:
-        _save_metadata(self, path, overwrite)
-        os.makedirs(os.path.join(path, "data"), exist_ok=True)
-        with open(os.path.join(path, "data", "part-00000"), "w") as f:
-            f.write(json.dumps(self._get_model_attributes()))
+        w = self.write()
+        (w.overwrite() if overwrite else w).save(path)
 
-    def write(self) -> _Writer:
-        return _Writer(self)
+    def write(self) -> Any:
+        if _spark_context_active():
+            from . import spark_binding
+
+            return spark_binding.make_writer(self, self._get_model_attributes())
+        return _Writer(self, self._get_model_attributes())
+
+    @classmethod
+    def read(cls) -> Any:
+        if _spark_context_active():
+            from . import spark_binding
+
+            return spark_binding.make_reader(cls, True)
+        return _Reader(cls, True)
 
     @classmethod
     def load(cls, path: str) -> "_CumlModel":
-        meta = _load_metadata(path)
-        with open(os.path.join(path, "data", "part-00000")) as f:
-            attrs = json.loads(f.read())
-        inst = cls(**attrs)
-        inst.uid = meta["uid"]
-        _set_params_from_metadata(inst, meta)
-        return inst
+        return cls.read().load(path)
 
     if not HAVE_PYSPARK:   # pyspark.ml.Transformer.transform(dataset, params) -> self._transform(dataset) otherwise
         def transform(self, dataset: LocalDataFrame) -> LocalDataFrame:

@@ -8,6 +8,8 @@ What the reference does at these call sites, reproduced here against the public 
   * barrier fit stage   core.py:1005-1013 dataset.mapInPandas(_train_udf, schema).rdd.barrier().mapPartitions(identity)
   * local-mode probe    core.py:377-384 / utils._is_local: master URL "local..." -> partition id doubles as the GPU id
   * transform           core.py:1846-1878 a pandas_udf over struct(*feature columns), appended with withColumn
+  * persistence         core.py:268-355   MLWriter / MLReader over DefaultParamsWriter.saveMetadata / DefaultParamsReader
+                                          (+ sc.parallelize([json]).saveAsTextFile(path/data) for a model)
 """
 from __future__ import annotations
 
@@ -120,3 +122,48 @@ def transform_with_pandas_udf(model: Any, dataset: Any, data_alias: str, set_gpu
 
     pred_name = model.getOrDefault("predictionCol")
     return dataset.withColumn(pred_name, predict_udf(struct(*select_cols)))
+
+
+def _extra_metadata(inst: Any) -> dict:
+    return {"_cuml_params": inst._cuml_params, "_num_workers": inst._num_workers, "_float32_inputs": inst._float32_inputs}
+
+
+def make_writer(inst: Any, model_attributes: Optional[dict]) -> Any:
+    """MLWriter for an estimator (model_attributes None) or a model — reference core.py:268-288, 310-332."""
+    import json
+    import os
+
+    from pyspark.ml.util import DefaultParamsWriter, MLWriter
+
+    class _B2kWriter(MLWriter):
+        def saveImpl(self, path: str) -> None:
+            DefaultParamsWriter.saveMetadata(inst, path, self.sc, extraMetadata=_extra_metadata(inst))
+            if model_attributes is not None:
+                self.sc.parallelize([json.dumps(model_attributes)], 1).saveAsTextFile(os.path.join(path, "data"))
+
+    return _B2kWriter()
+
+
+def make_reader(cls: Any, is_model: bool) -> Any:
+    """MLReader for an estimator or a model class — reference core.py:291-307, 335-355."""
+    import json
+    import os
+
+    from pyspark.ml.util import DefaultParamsReader, MLReader
+
+    class _B2kReader(MLReader):
+        def load(self, path: str) -> Any:
+            metadata = DefaultParamsReader.loadMetadata(path, self.sc)
+            if is_model:
+                attrs = json.loads(self.sc.textFile(os.path.join(path, "data")).collect()[0])
+                inst = cls(**attrs)
+            else:
+                inst = cls()
+            inst._resetUid(metadata["uid"])
+            DefaultParamsReader.getAndSetParams(inst, metadata)
+            inst._cuml_params = metadata["_cuml_params"]
+            inst._num_workers = metadata["_num_workers"]
+            inst._float32_inputs = metadata["_float32_inputs"]
+            return inst
+
+    return _B2kReader()

@@ -127,6 +127,20 @@ class Params:
             m.update(extra)
         return m
 
+    def _resetUid(self, newUid: str) -> "Params":
+        """pyspark.ml.param.Params._resetUid: change the uid and re-parent every Param (and the two maps)."""
+        newUid = str(newUid)
+        self.uid = newUid
+        remap: Dict[Param, Param] = {}
+        for name, val in list(self.__dict__.items()):
+            if isinstance(val, Param):
+                q = Param(self, val.name, val.doc, val.typeConverter)
+                remap[val] = q
+                setattr(self, name, q)
+        self._paramMap = {remap.get(p, p): v for p, v in self._paramMap.items()}
+        self._defaultParamMap = {remap.get(p, p): v for p, v in self._defaultParamMap.items()}
+        return self
+
     # --- mutation ---
     def _set(self, **kwargs: Any) -> "Params":
         for name, value in kwargs.items():

@@ -21,6 +21,46 @@ def keyword_only(func):
     return wrapper
 
 
+class _TextRDD:
+    def __init__(self, lines, path=None):
+        self._lines, self._path = lines, path
+
+    def saveAsTextFile(self, path):
+        import os
+
+        CALLS.append(("rdd.saveAsTextFile", path))
+        os.makedirs(path)
+        with open(os.path.join(path, "part-00000"), "w") as f:
+            f.write("".join(l + "\n" for l in self._lines))
+        open(os.path.join(path, "_SUCCESS"), "w").close()
+
+    def collect(self):
+        return list(self._lines)
+
+    def first(self):
+        return self._lines[0]
+
+
+class SparkContext:
+    _active_spark_context = None   # tests that exercise persistence through Spark install one
+    master = "local[1]"
+
+    def parallelize(self, data, numSlices=None):
+        CALLS.append(("sc.parallelize", numSlices))
+        return _TextRDD(list(data))
+
+    def textFile(self, path):
+        import os
+
+        CALLS.append(("sc.textFile", path))
+        lines = []
+        for name in sorted(os.listdir(path)):
+            if name.startswith("part-"):
+                with open(os.path.join(path, name)) as f:
+                    lines += [l.rstrip("\n") for l in f if l.strip()]
+        return _TextRDD(lines, path)
+
+
 class TaskContext:
     _pid = 0
 

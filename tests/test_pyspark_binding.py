@@ -140,3 +140,95 @@ def test_pyspark_branch_wiring_with_host_stand_ins():
 def test_pyspark_branch_end_to_end_on_gpu():
     """Same plan, nothing replaced: the worker function ingests the Arrow batches on the device and calls libb2kmeans."""
     _check(_run(_COMMON + _BODY))
+
+
+_PERSIST = '''
+import os, tempfile
+from pyspark import SparkContext
+SparkContext._active_spark_context = SparkContext()      # a live SparkContext: persistence goes through pyspark.ml.util
+import pyspark.ml.util as U
+root = tempfile.mkdtemp()
+km = KMeans(k=4, maxIter=9, seed=2, num_workers=1).setFeaturesCol("f")
+del CALLS[:]
+w = km.write()
+assert isinstance(w, U.MLWriter)
+w.overwrite().save(os.path.join(root, "est"))
+est_calls = [c[0] for c in CALLS]
+km2 = KMeans.load(os.path.join(root, "est"))
+m = KMeansModel(cluster_centers_=[[0.0, 1.0], [2.0, 3.0]], n_cols=2, dtype="float32")
+m._set(featuresCol="f")
+del CALLS[:]
+m.write().overwrite().save(os.path.join(root, "model"))
+model_calls = [c[0] for c in CALLS]
+del CALLS[:]
+r = KMeansModel.read()
+assert isinstance(r, U.MLReader)
+m2 = r.load(os.path.join(root, "model"))
+load_calls = [c[0] for c in CALLS]
+# what the Spark-side writer left on disk is also what the local reader accepts (and the reference's layout)
+SparkContext._active_spark_context = None
+m3 = KMeansModel.load(os.path.join(root, "model"))
+print("RESULT " + json.dumps({
+    "est_calls": est_calls, "model_calls": model_calls, "load_calls": load_calls,
+    "est_ok": km2.uid == km.uid and km2.getK() == 4 and km2.getMaxIter() == 9 and km2.getFeaturesCol() == "f"
+              and km2.cuml_params["n_clusters"] == 4,
+    "model_ok": m2.uid == m.uid and m2.cluster_centers_ == m.cluster_centers_ and m2.getFeaturesCol() == "f",
+    "local_reads_spark_layout": m3.uid == m.uid and m3.cluster_centers_ == m.cluster_centers_,
+    "files": sorted(os.listdir(os.path.join(root, "model"))),
+}))
+'''
+
+_INSTALL = '''
+import pyspark.ml.clustering as stock_mod
+StockKMeans = stock_mod.KMeans
+import spark_rapids_ml_b200.install as inst
+from pyspark.ml.clustering import KMeans as K1, KMeansModel as M1, BisectingKMeans as B1
+import pyspark.ml.clustering as proxied
+import pyspark.ml
+from pyspark.ml.clustering import _sibling_lookup
+res = {
+    "user_import_is_accelerated": K1 is KMeans and M1 is KMeansModel,
+    "attribute_access_is_accelerated": proxied.KMeans is KMeans and pyspark.ml.clustering.KMeans is KMeans,
+    "other_names_untouched": getattr(B1, "stock", False) is True,
+    "pyspark_ml_itself_sees_stock": _sibling_lookup() is StockKMeans,
+    "this_package_sees_stock": inst._called_from_library.__module__ == "spark_rapids_ml_b200.install",
+    "missing_attr_raises": False,
+}
+try:
+    proxied.NoSuchThing
+except AttributeError:
+    res["missing_attr_raises"] = True
+inst.install()                                   # idempotent
+res["idempotent"] = proxied is sys.modules["pyspark.ml.clustering"]
+inst.uninstall()
+res["uninstall_restores"] = sys.modules["pyspark.ml.clustering"].KMeans is StockKMeans
+# python -m spark_rapids_ml_b200 script.py: the script's plain pyspark import is the accelerated class
+import os, tempfile, subprocess
+d = tempfile.mkdtemp()
+with open(os.path.join(d, "user_script.py"), "w") as f:
+    f.write("import sys\\nfrom pyspark.ml.clustering import KMeans\\nprint('SCRIPT', KMeans.__module__, sys.argv[1:])\\n")
+out = subprocess.run([sys.executable, "-m", "spark_rapids_ml_b200", os.path.join(d, "user_script.py"), "a", "b"],
+                     capture_output=True, text=True, env=os.environ)
+res["runner_output"] = [l for l in out.stdout.splitlines() if l.startswith("SCRIPT")] or [out.stderr[-300:]]
+print("RESULT " + json.dumps(res))
+'''
+
+
+def test_pyspark_branch_persistence_goes_through_mlwriter():
+    r = _run(_COMMON + _PERSIST)
+    assert r["est_calls"][:2] == ["MLWriter.save", "DefaultParamsWriter.saveMetadata"], r
+    mc = r["model_calls"]
+    assert mc.index("DefaultParamsWriter.saveMetadata") < mc.index("rdd.saveAsTextFile"), r
+    assert mc.count("rdd.saveAsTextFile") == 2 and "sc.parallelize" in mc, r          # metadata + data
+    lc = r["load_calls"]
+    assert lc.index("DefaultParamsReader.loadMetadata") < lc.index("DefaultParamsReader.getAndSetParams"), r
+    assert "sc.textFile" in lc, r
+    assert r["est_ok"] and r["model_ok"] and r["local_reads_spark_layout"] and r["files"] == ["data", "metadata"], r
+
+
+def test_install_proxy_swaps_kmeans_for_user_code_only():
+    r = _run(_COMMON + _INSTALL)
+    for key in ("user_import_is_accelerated", "attribute_access_is_accelerated", "other_names_untouched",
+                "pyspark_ml_itself_sees_stock", "missing_attr_raises", "idempotent", "uninstall_restores"):
+        assert r[key] is True, (key, r)
+    assert r["runner_output"] == ["SCRIPT spark_rapids_ml_b200.clustering ['a', 'b']"], r
