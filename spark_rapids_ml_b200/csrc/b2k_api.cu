@@ -779,14 +779,23 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(&phi, phi_dev, 8, cudaMemcpyDeviceToHost, s));
     B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
     if (!(phi > 0)) break;
-    B2K_CUDA_OK(ctx, cudaMemsetAsync(n_picked_dev, 0, sizeof(int), s));
-    B2K_TRY(b2k_launch_bernoulli_pick(ctx, mind, n, rows.offset, ell / phi, seed, r, idx_dev, n_picked_dev, cap, s));
+    // The pick kernel stores at most cap entries and WHICH ones it keeps on overflow depends on atomic slot order, so an
+    // overflowing draw (expected ell picks against cap = 4 ell + 64: essentially never) is repeated with a smaller
+    // probability scale: the draw is keyed on (seed, round, global row), so the smaller draw is a subset and the
+    // candidate set stays a deterministic function of the seed.
+    double scale = ell / phi;
     int np = 0;
-    B2K_CUDA_OK(ctx, cudaMemcpyAsync(&np, n_picked_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-    B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    np = std::min(np, cap);   // the pick kernel stores at most cap entries; which ones is slot-order dependent, so ...
+    for (int attempt = 0; attempt < 8; ++attempt) {
+      B2K_CUDA_OK(ctx, cudaMemsetAsync(n_picked_dev, 0, sizeof(int), s));
+      B2K_TRY(b2k_launch_bernoulli_pick(ctx, mind, n, rows.offset, scale, seed, r, idx_dev, n_picked_dev, cap, s));
+      B2K_CUDA_OK(ctx, cudaMemcpyAsync(&np, n_picked_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B2K_CUDA_OK(ctx, cudaStreamSynchronize(s));
+      if (np <= cap) break;
+      scale *= 0.75 * (double)cap / (double)np;
+    }
+    np = std::min(np, cap);
     if (np > 0) B2K_CUDA_OK(ctx, cudaMemcpy(picked_host.data(), idx_dev, (size_t)np * 8, cudaMemcpyDeviceToHost));
-    std::sort(picked_host.begin(), picked_host.begin() + np);   // ... the order at least is canonical
+    std::sort(picked_host.begin(), picked_host.begin() + np);   // slot order -> canonical order
     // exchange: every rank learns every rank's picks (global indices), capped in total
     std::vector<int64_t> all;
     if (ctx->nranks == 1) {
