@@ -74,6 +74,7 @@ extern "C" int b2k_ctx_destroy(b2k_ctx* ctx) {
   b2k_copy_pool_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->prof_dev) cudaFree(ctx->prof_dev);
+  if (ctx->xnorm_cache) cudaFree(ctx->xnorm_cache);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->dev_stage[i]) cudaFree(ctx->dev_stage[i]);
@@ -730,12 +731,12 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
   const int cap = (int)std::min<int64_t>(rows.total, (int64_t)(4 * ell) + 64);  // per-round candidate cap
   const int Mmax = 1 + rounds * cap + k;
   // scratch (all taken from one arena sized from cap / nranks: no fixed-offset control region):
-  //   idx[cap+8] | n_picked | phi | blocks[1024] | exchange[(cap+1)*(nranks+1)] | mind[n] | dn[n] | labels[n] |
+  //   idx[cap+8] | n_picked | phi | blocks[1024] | exchange[(cap+1)*(nranks+1)] | mind[n] | dn[n] | labels[n] | lab_new[n] |
   //   cand[Mmax*d] | newc[cap*d] | hist[Mmax] | assign scratch
   size_t nn = (size_t)(n > 0 ? n : 1);
   const size_t per = (size_t)cap + 1;   // [count | cap indices] per rank in the candidate exchange
   size_t fixed = align_up((size_t)(cap + 8) * 8, 256) + 256 + 256 + align_up(1024 * 8, 256) +
-                 align_up(per * (size_t)(ctx->nranks + 1) * 8, 256) + 3 * align_up(nn * 4, 256) +
+                 align_up(per * (size_t)(ctx->nranks + 1) * 8, 256) + 4 * align_up(nn * 4, 256) +
                  align_up((size_t)Mmax * d * 4, 256) + align_up((size_t)cap * d * 4, 256) +
                  align_up((size_t)Mmax * 8, 256) + 8192;
   // the assign passes below run with 1 .. Mmax centres: small counts take a fused kernel (its scratch holds per-CTA
@@ -752,7 +753,8 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
   int64_t* xchg = A.take<int64_t>(per * (size_t)(ctx->nranks + 1));
   float* mind = A.take<float>(nn);
   float* dn = A.take<float>(nn);
-  int32_t* labels = A.take<int32_t>(nn);
+  int32_t* labels = A.take<int32_t>(nn);    // running nearest candidate of every row (global candidate index)
+  int32_t* lab_new = A.take<int32_t>(nn);   // nearest among one round's new candidates
   float* cand = A.take<float>((size_t)Mmax * d);
   float* newc = A.take<float>((size_t)cap * d);
   double* hist = A.take<double>(Mmax);
@@ -766,6 +768,7 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
     B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, g, cand, idx_dev, s));
     M = 1;
     B2K_TRY(assign_impl(ctx, X, n, d, cand, 1, nullptr, mind, phi_dev, assign_off, s));
+    B2K_CUDA_OK(ctx, cudaMemsetAsync(labels, 0, nn * 4, s));   // every row is nearest to candidate 0 so far
   }
   std::vector<int64_t> picked_host(cap);
   std::vector<int64_t> counts_host(ctx->nranks);
@@ -823,17 +826,20 @@ static int init_kmeans_parallel(b2k_ctx* ctx, const float* X, int64_t n, int d, 
     const int m = (int)all.size();
     B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, all, newc, idx_dev, s));
     B2K_CUDA_OK(ctx, cudaMemcpyAsync(cand + (size_t)M * d, newc, (size_t)m * d * 4, cudaMemcpyDeviceToDevice, s));
+    // nearest among the new candidates, folded into the running (min distance, nearest candidate): strict '<' keeps the
+    // earlier candidate on ties, so after the last round `labels` IS the argmin over all candidates — the k-means||
+    // weights need no extra pass over X
+    B2K_TRY(assign_impl(ctx, X, n, d, newc, m, lab_new, dn, nullptr, assign_off, s));
+    B2K_TRY(b2k_launch_merge_chunk(ctx, mind, labels, dn, lab_new, M, n, nullptr, s));
     M += m;
-    B2K_TRY(assign_impl(ctx, X, n, d, newc, m, nullptr, dn, nullptr, assign_off, s));
-    B2K_TRY(b2k_launch_min_inplace(ctx, mind, dn, n, s));
   }
-  if (M < k) {  // top up with distinct random rows so that M >= k
+  if (M < k) {  // top up with distinct random rows so that M >= k (tiny inputs): these need one full assignment
     std::vector<int64_t> extra = sample_distinct(rng, rows.total, k - M + 1);
     B2K_TRY(fetch_global_rows(ctx, X, n, d, rows, extra, cand + (size_t)M * d, idx_dev, s));
     M += (int)extra.size();
+    B2K_TRY(assign_impl(ctx, X, n, d, cand, M, labels, nullptr, nullptr, assign_off, s));
   }
-  // weights = #points closest to each candidate
-  B2K_TRY(assign_impl(ctx, X, n, d, cand, M, labels, nullptr, nullptr, assign_off, s));
+  // weights = #points closest to each candidate (the running argmin of the rounds)
   B2K_TRY(b2k_launch_histogram(ctx, labels, n, M, hist, s));
   if (ctx->nranks > 1) B2K_TRY(b2k_comm_allreduce_f64(ctx, hist, M, s));
   std::vector<float> P((size_t)M * d);
@@ -900,6 +906,19 @@ extern "C" int b2k_kmeans_fit(b2k_ctx* ctx, const float* X, int64_t n_local, int
         return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: empty partition (rank " + std::to_string(r) +
                                                   " has n_local == 0)");
   }
+  struct NormScope {   // see b2k_ctx::xnorm_scope_X
+    b2k_ctx* c;
+    NormScope(b2k_ctx* c_, const float* X_, int64_t n_, int d_) : c(c_) {
+      c->xnorm_scope_X = X_;
+      c->xnorm_scope_n = n_;
+      c->xnorm_scope_d = d_;
+      c->xnorm_cache_valid = 0;
+    }
+    ~NormScope() {
+      c->xnorm_scope_X = nullptr;
+      c->xnorm_cache_valid = 0;
+    }
+  } norm_scope(ctx, X, n_local, d);
   switch (init_mode) {
     case B2K_INIT_ARRAY:
       if (!init_centers) return b2k_fail(ctx, B2K_ERR_INVALID, "b2k_kmeans_fit: init_centers is NULL");

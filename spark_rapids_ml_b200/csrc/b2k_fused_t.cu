@@ -1147,14 +1147,33 @@ void b2k_fused_t_views(const B2kFusedPlan& plan, void* plan_scratch, int64_t n, 
   if (rstat) *rstat = reinterpret_cast<unsigned long long*>(b + L.off_rstat);
 }
 
-// once per fit / lloyd / assign call: row norms of X into the plan scratch; clears the recheck counters
+static bool xnorm_in_scope(const b2k_ctx* ctx, const float* X, int64_t n, int d) {
+  return ctx->xnorm_scope_X != nullptr && ctx->xnorm_scope_X == X && ctx->xnorm_scope_n == n && ctx->xnorm_scope_d == d;
+}
+
+// once per fit / lloyd / assign call: row norms of X into the plan scratch (or, inside b2k_kmeans_fit, once per fit into
+// the context's cache); clears the recheck counters
 int b2k_fused_t_prepare(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratch, const float* X, int64_t n, int d,
                         int k, cudaStream_t s) {
   TLayout L = t_layout(plan, n, k, d);
   char* b = static_cast<char*>(plan_scratch);
   B2K_CUDA_OK(ctx, cudaMemsetAsync(b + L.off_rstat, 0, 16, s));
   int blocks = ctx->sm_count * 8;
-  k_row_norms<<<blocks, 256, 0, s>>>(X, n, d, reinterpret_cast<float2*>(b + L.off_xnorm));
+  float2* dst = reinterpret_cast<float2*>(b + L.off_xnorm);
+  if (xnorm_in_scope(ctx, X, n, d)) {   // inside one b2k_kmeans_fit: one norms pass for all of its passes over X
+    if (ctx->xnorm_cache_rows < n) {
+      if (ctx->xnorm_cache) cudaFree(ctx->xnorm_cache);
+      ctx->xnorm_cache = nullptr;
+      ctx->xnorm_cache_rows = 0;
+      B2K_CUDA_OK(ctx, cudaMalloc(&ctx->xnorm_cache, (size_t)n * sizeof(float2)));
+      ctx->xnorm_cache_rows = n;
+      ctx->xnorm_cache_valid = 0;
+    }
+    if (ctx->xnorm_cache_valid) return B2K_OK;
+    dst = static_cast<float2*>(ctx->xnorm_cache);
+    ctx->xnorm_cache_valid = 1;
+  }
+  k_row_norms<<<blocks, 256, 0, s>>>(X, n, d, dst);
   ctx->stats.kernel_launches++;
   B2K_CUDA_OK(ctx, cudaGetLastError());
   return B2K_OK;
@@ -1187,7 +1206,8 @@ int b2k_launch_fused_t(b2k_ctx* ctx, const B2kFusedPlan& plan, void* plan_scratc
   a.C32 = C;
   a.cnorm = cnorm;
   a.thr = thr;
-  a.xnorm = reinterpret_cast<const float2*>(b + L.off_xnorm);
+  a.xnorm = (xnorm_in_scope(ctx, X, n, d) && ctx->xnorm_cache_valid) ? static_cast<const float2*>(ctx->xnorm_cache)
+                                                                      : reinterpret_cast<const float2*>(b + L.off_xnorm);
   a.keytab = keytab;
   a.keyinv = keytab + 256;
   a.partials = reinterpret_cast<float*>(b + L.off_partials);

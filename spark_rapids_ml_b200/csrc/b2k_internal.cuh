@@ -52,6 +52,14 @@ struct b2k_ctx {
   int collect_recheck = 0;       // option "collect_recheck": fill stats.recheck_* (costs a stream sync per call)
   int want_cost = 1;             // assign passes: compute the cost partial (set by assign_impl)
   int profile_fused = 0;         // record per-role blocked-cycle counters of the fused kernel
+  // Row norms of the large-shape kernel, shared by every pass of ONE b2k_kmeans_fit call (k-means|| candidate passes,
+  // the Lloyd loop, the inertia pass all see the same immutable X): computed by the first pass, reused by the rest.
+  const float* xnorm_scope_X = nullptr;   // non-null only inside b2k_kmeans_fit
+  int64_t xnorm_scope_n = 0;
+  int xnorm_scope_d = 0;
+  void* xnorm_cache = nullptr;            // float2 [xnorm_cache_rows]
+  int64_t xnorm_cache_rows = 0;
+  int xnorm_cache_valid = 0;
   long long* prof_dev = nullptr;  // [grid][18 warps][8]
   int prof_grid = 0;
   // comm
