@@ -127,6 +127,7 @@ class KMeans(KMeansClass, _CumlEstimator, _KMeansCumlParams):
                  seed: Optional[int] = None, num_workers: Optional[int] = None,
                  verbose: Union[int, bool] = False, **kwargs: Any) -> None:
         super().__init__()
+        self._handle_param_spark_confs()   # session-wide defaults for arguments not passed (clustering.py:315)
         # if the user does not override it, n_init = 1 to match Spark behaviour (clustering.py:316-319)
         if "n_init" not in self._input_kwargs:
             self._input_kwargs["n_init"] = 1

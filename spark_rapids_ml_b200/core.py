@@ -278,10 +278,38 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
     def _merge_model_chunks(self, rows: List[Row], paramMaps: Optional[Sequence[Dict[Any, Any]]] = None) -> List[Row]:
         return rows
 
+    def _handle_param_spark_confs(self) -> None:
+        """Constructor arguments the user did NOT pass may be given session-wide through Spark confs — the only way to set
+        them under Spark Connect (reference core.py:1124-1170): spark.rapids.ml.verbose (bool or 0..6),
+        spark.rapids.ml.float32_inputs (bool), spark.rapids.ml.num_workers (int > 0).  Values land in _input_kwargs
+        before _set_params reads them; an explicit argument always wins."""
+        conf = _active_session_conf()
+        if conf is None:
+            return
+        kw = self._input_kwargs
+        for name, key, parse, expects in _CONF_PARAMS:
+            raw = conf.get(key, None)
+            if kw.get(name) is not None or raw is None:   # an explicit argument always wins
+                continue
+            try:
+                kw[name] = parse(str(raw).strip().lower())
+            except Exception:
+                raise ValueError(f"Invalid value for {key} which should be {expects}: {raw}") from None
+
     def _fit_internal(self, dataset: LocalDataFrame, paramMaps: Optional[Sequence[Dict[Any, Any]]]) -> List["_CumlModel"]:
         self.logger.info(f"Training spark-rapids-ml (b200) with {self.num_workers} worker(s) ...")
-        res = self._call_cuml_fit_func(dataset=dataset, partially_collect=True, paramMaps=paramMaps)
-        rows = res if isinstance(res, list) else res.collect()   # the pyspark branch returns the collected rows
+        try:
+            res = self._call_cuml_fit_func(dataset=dataset, partially_collect=True, paramMaps=paramMaps)
+            rows = res if isinstance(res, list) else res.collect()   # the pyspark branch returns the collected rows
+        except Exception as e:
+            # Spark refuses a barrier stage on some RDD chains (e.g. after coalesce): retry once on a repartitioned
+            # dataset, as the reference does (core.py:1245-1257)
+            if "BarrierJobUnsupportedRDDChainException" not in str(e):
+                raise
+            self.logger.warning("Barrier rdd error encountered with input dataset. Retrying with repartitioning.")
+            res = self._call_cuml_fit_func(dataset=dataset.repartition(self.num_workers), partially_collect=True,
+                                           paramMaps=paramMaps)
+            rows = res if isinstance(res, list) else res.collect()
         self.logger.info("Finished training")
         rows = self._merge_model_chunks(rows, paramMaps)
         models: List["_CumlModel"] = []
@@ -328,6 +356,52 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
     @classmethod
     def load(cls, path: str) -> "_CumlEstimator":
         return cls.read().load(path)
+
+
+def _parse_conf_bool(v: str) -> bool:
+    if v not in ("true", "false"):
+        raise ValueError(v)
+    return v == "true"
+
+
+def _parse_conf_verbose(v: str) -> Union[int, bool]:
+    try:
+        i = int(v)
+    except ValueError:
+        return _parse_conf_bool(v)
+    if not 0 <= i <= 6:
+        raise ValueError(v)
+    return i
+
+
+def _parse_conf_pos_int(v: str) -> int:
+    i = int(v)
+    if i <= 0:
+        raise ValueError(v)
+    return i
+
+
+_CONF_PARAMS = (
+    ("verbose", "spark.rapids.ml.verbose", _parse_conf_verbose, "a boolean or an integer between 0 and 6"),
+    ("float32_inputs", "spark.rapids.ml.float32_inputs", _parse_conf_bool, "a boolean"),
+    ("num_workers", "spark.rapids.ml.num_workers", _parse_conf_pos_int, "an integer greater than 0"),
+)
+
+
+def _active_session_conf() -> Any:
+    """The conf of the active session, without creating one: the live SparkSession under pyspark, else the LocalSession."""
+    if HAVE_PYSPARK:
+        try:
+            from pyspark.sql import SparkSession
+
+            active = SparkSession.getActiveSession()
+            if active is not None:
+                return active.conf
+        except Exception:
+            pass
+    from .sparkshim.sql import LocalSession
+
+    return LocalSession._active.conf if LocalSession._active is not None else None
 
 
 def _spark_context_active() -> bool:

@@ -71,14 +71,19 @@ class LocalSession:
             table = data
         else:
             rows = list(data)
-            names = list(schema) if schema is not None else [f"_{i + 1}" for i in range(len(rows[0]))]
+            types: List[Optional[pa.DataType]]
+            if isinstance(schema, str):   # Spark DDL: "c1 int, c2 int" / "features array<float>, label float"
+                names, types = _parse_ddl(schema)
+            else:
+                names = list(schema) if schema is not None else [f"_{i + 1}" for i in range(len(rows[0]))]
+                types = [None] * len(names)
             cols = list(zip(*rows)) if rows else [[] for _ in names]
             arrays = []
-            for c in cols:
+            for c, t in zip(cols, types):
                 c = list(c)
                 if len(c) and hasattr(c[0], "toArray"):  # pyspark.ml.linalg vectors, if someone passes them
                     c = [v.toArray().tolist() for v in c]
-                arrays.append(pa.array(c))
+                arrays.append(pa.array(c, type=t) if t is not None else pa.array(c))
             table = pa.Table.from_arrays(arrays, names=names)
         return LocalDataFrame(self, _split_table(table, num_partitions, self.max_records_per_batch))
 
@@ -95,6 +100,40 @@ class LocalSession:
             arrays.append(pa.array(v))
         return LocalDataFrame(self, _split_table(pa.Table.from_arrays(arrays, names=names), num_partitions,
                                                  self.max_records_per_batch))
+
+
+_DDL_TYPES = {"byte": pa.int8(), "tinyint": pa.int8(), "short": pa.int16(), "smallint": pa.int16(), "int": pa.int32(),
+              "integer": pa.int32(), "long": pa.int64(), "bigint": pa.int64(), "float": pa.float32(), "real": pa.float32(),
+              "double": pa.float64(), "string": pa.string(), "boolean": pa.bool_()}
+
+
+def _parse_ddl(schema: str) -> Tuple[List[str], List[Optional[pa.DataType]]]:
+    """The subset of Spark's DDL schema strings the KMeans tests use: `name type` pairs, scalar types and array<scalar>."""
+    names: List[str] = []
+    types: List[Optional[pa.DataType]] = []
+    depth, start, fields = 0, 0, []
+    for i, ch in enumerate(schema):   # split on commas outside <...>
+        depth += ch == "<"
+        depth -= ch == ">"
+        if ch == "," and depth == 0:
+            fields.append(schema[start:i])
+            start = i + 1
+    fields.append(schema[start:])
+    for f in fields:
+        name, _, tname = f.strip().partition(" ")
+        tname = tname.strip().lower()
+        if tname.startswith("array<") and tname.endswith(">"):
+            inner = _DDL_TYPES.get(tname[6:-1].strip())
+            if inner is None:
+                raise ValueError(f"unsupported element type in schema field '{f.strip()}'")
+            t: Optional[pa.DataType] = pa.list_(inner)
+        else:
+            t = _DDL_TYPES.get(tname)
+            if t is None:
+                raise ValueError(f"unsupported type in schema field '{f.strip()}'")
+        names.append(name)
+        types.append(t)
+    return names, types
 
 
 def get_session() -> LocalSession:

@@ -55,17 +55,25 @@ class RDD:
         CALLS.append(("rdd.collect", None))
         fn, schema = self._df._pending
         assert self._barrier, "the fit stage must be a barrier stage"
+        if self._df._coalesced:
+            raise RuntimeError("org.apache.spark.scheduler.BarrierJobUnsupportedRDDChainException: [SPARK-24820][SPARK-24821]: "
+                               "Barrier execution mode does not allow the following pattern of RDD chain within a barrier stage")
         return self._df._local.mapInPandas(fn, schema=schema, barrier=True).collect()
 
 
 class DataFrame:
     """Wraps a LocalDataFrame; `vector_cols`: columns presented as VectorUDT (stored as array<double>)."""
 
-    def __init__(self, local, vector_cols=()):
+    def __init__(self, local, vector_cols=(), coalesced=False):
         self._local = local
         self._vector_cols = set(vector_cols)
         self._pending = None
+        self._coalesced = coalesced   # Spark refuses a barrier stage on a coalesced RDD chain
         self.sparkSession = SparkSession()
+
+    def coalesce(self, n):
+        CALLS.append(("coalesce", n))
+        return DataFrame(self._local.repartition(n), self._vector_cols, coalesced=True)
 
     @property
     def schema(self):
@@ -92,7 +100,7 @@ class DataFrame:
                 df = df.cast_column(c.name, t)
             if c.out_name != c.name:
                 df = df.withColumnRenamed(c.name, c.out_name)
-        return DataFrame(df)
+        return DataFrame(df, coalesced=self._coalesced)
 
     def first(self):
         return self._local.first()
@@ -103,7 +111,7 @@ class DataFrame:
 
     def mapInPandas(self, fn, schema=None):
         CALLS.append(("mapInPandas", str(schema)))
-        out = DataFrame(self._local, self._vector_cols)
+        out = DataFrame(self._local, self._vector_cols, coalesced=self._coalesced)
         out._pending = (fn, schema)
         return out
 

@@ -88,3 +88,52 @@ def test_empty_partition_raises(session):
     df._parts = [[]]                      # a partition whose Arrow stream is empty (core.py:959-962)
     with pytest.raises(RuntimeError, match="no data"):
         KMeans(k=2, num_workers=1).fit(df)
+
+
+@pytest.mark.parametrize("data_type", ["byte", "short", "int", "long"])
+def test_integer_feature_columns(session, data_type):
+    """reference tests/test_kmeans.py:312-335 (test_kmeans_numeric_type): scalar integer columns are accepted (cast to
+    float32 on the way in) — here also checked against the oracle on the same five rows."""
+    from spark_rapids_ml_b200.clustering import KMeans
+
+    data = [[1, 4, 4, 4, 0], [2, 2, 2, 2, 1], [3, 3, 3, 2, 2], [3, 3, 3, 2, 3], [5, 2, 1, 3, 4]]
+    cols = ["c1", "c2", "c3", "c4", "c5"]
+    df = session.createDataFrame(data, schema=", ".join(f"{c} {data_type}" for c in cols))
+    model = KMeans(num_workers=1, featuresCols=cols, n_clusters=2, initMode="random", seed=1, maxIter=10).fit(df)
+    assert model.n_cols == 5 and model.dtype == "float32"
+    X = np.asarray(data, dtype=np.float32)
+    C = np.asarray(model.cluster_centers_, dtype=np.float64)
+    lab, _, _ = ko.assign(X, C.astype(np.float32))
+    for j in range(2):                              # a fixed point of Lloyd on these rows: centres = means of their rows
+        assert (lab == j).any() and np.allclose(C[j], X[lab == j].mean(0), rtol=1e-5)
+    out = model.transform(df)
+    assert [r["prediction"] for r in out.collect()] == lab.tolist()
+
+
+def test_parameters_validation(session):
+    """reference tests/test_kmeans.py:529-546: k = -1 / maxIter = -1 are refused with Spark's wording."""
+    from spark_rapids_ml_b200.clustering import KMeans
+
+    df = session.createDataFrame([([1.0, 2.0], 1.0), ([3.0, 1.0], 0.0)], schema="features array<float>, label float")
+    with pytest.raises(ValueError, match="k given invalid value -1"):
+        KMeans(k=-1, num_workers=1).fit(df)
+    with pytest.raises(ValueError, match="maxIter given invalid value -1"):
+        KMeans(num_workers=1).setMaxIter(-1).fit(df)
+
+
+def test_session_confs_reach_the_fit(tmp_path):
+    """spark.rapids.ml.float32_inputs = false from the session conf: the model is fit and stored in float64 columns'
+    dtype, as with the constructor argument (reference core.py:1149-1159)."""
+    from spark_rapids_ml_b200.clustering import KMeans
+    from spark_rapids_ml_b200.sparkshim import LocalSession
+
+    sess = LocalSession({"spark.rapids.ml.float32_inputs": "false"})
+    try:
+        X, _ = ko.make_blobs(400, 8, 3, seed=2)
+        df = sess.createDataFrame([(r.astype(np.float64).tolist(),) for r in X], schema="features array<double>")
+        est = KMeans(k=3, num_workers=1, seed=1, initMode="random")
+        assert est._float32_inputs is False
+        model = est.fit(df)
+        assert model.dtype == "float64" and model._float32_inputs is False
+    finally:
+        LocalSession()

@@ -101,3 +101,34 @@ def test_merge_model_chunks_orders_by_chunk_id():
     assert merged[0]["cluster_centers_"] == [[1.0], [2.0], [3.0]]
     with pytest.raises(ValueError):
         KMeans()._merge_model_chunks([])
+
+
+def test_constructor_defaults_from_session_confs():
+    """reference core.py:1124-1170 / tests/test_kmeans.py:590-660: spark.rapids.ml.{verbose,float32_inputs,num_workers}
+    fill in constructor arguments the user did not pass; explicit arguments win; bad values are loud."""
+    import pytest
+    from spark_rapids_ml_b200.sparkshim import LocalSession
+    from spark_rapids_ml_b200.sparkshim.sql import LocalSession as LS
+
+    saved = LS._active
+    try:
+        LocalSession(conf={"spark.rapids.ml.verbose": "5", "spark.rapids.ml.float32_inputs": "false",
+                           "spark.rapids.ml.num_workers": "3"})
+        est = KMeans()
+        assert est._input_kwargs["verbose"] == 5 and est._input_kwargs["float32_inputs"] is False
+        assert est._input_kwargs["num_workers"] == 3
+        assert est._num_workers == 3 and est._float32_inputs is False and est.cuml_params["verbose"] == 5
+        est = KMeans(verbose=False, float32_inputs=True, num_workers=1)          # explicit arguments win
+        assert est._input_kwargs["verbose"] is False and est._float32_inputs is True and est._num_workers == 1
+        LocalSession(conf={"spark.rapids.ml.verbose": "TRUE"})
+        assert KMeans()._input_kwargs["verbose"] is True
+        for key, bad in (("spark.rapids.ml.verbose", "7"), ("spark.rapids.ml.verbose", "loud"),
+                         ("spark.rapids.ml.float32_inputs", "1"), ("spark.rapids.ml.num_workers", "0"),
+                         ("spark.rapids.ml.num_workers", "two")):
+            LocalSession(conf={key: bad})
+            with pytest.raises(ValueError, match="Invalid value for " + key.replace(".", r"\.")):
+                KMeans()
+        LocalSession()
+        assert "float32_inputs" not in KMeans()._input_kwargs                     # nothing set: nothing injected
+    finally:
+        LS._active = saved

@@ -232,3 +232,32 @@ def test_install_proxy_swaps_kmeans_for_user_code_only():
                 "pyspark_ml_itself_sees_stock", "missing_attr_raises", "idempotent", "uninstall_restores"):
         assert r[key] is True, (key, r)
     assert r["runner_output"] == ["SCRIPT spark_rapids_ml_b200.clustering ['a', 'b']"], r
+
+
+_RETRY = '''
+import logging
+records = []
+class H(logging.Handler):
+    def emit(self, r): records.append(r.getMessage())
+logging.getLogger().addHandler(H())
+local = sess.from_numpy(X.astype(np.float32), col="features", num_partitions=3)
+df = DataFrame(local).coalesce(1)                  # same partition count as num_workers: no repartition before the stage
+del CALLS[:]
+est = KMeans(k=4, maxIter=5, initMode="random", seed=1, num_workers=1).setFeaturesCol("features")
+est.logger.addHandler(H())
+model = est.fit(df)
+calls = [c[0] for c in CALLS]
+print("RESULT " + json.dumps({"calls": calls, "n_centers": len(model.cluster_centers_),
+                              "warned": any("Retrying with repartitioning" in m for m in records)}))
+'''
+
+
+def test_barrier_rdd_chain_error_is_retried_after_repartition():
+    """reference core.py:1245-1257 / tests/test_kmeans.py:285-310: a coalesced input makes Spark refuse the barrier stage;
+    the estimator logs the warning and fits the repartitioned dataset."""
+    r = _run(_COMMON + _CPU_STUBS + _RETRY)
+    c = r["calls"]
+    assert c.count("mapInPandas") == 2 and c.count("rdd.collect") == 2, r
+    first_collect = c.index("rdd.collect")
+    assert "repartition" in c[first_collect:] and "repartition" not in c[:first_collect], r
+    assert r["warned"] and r["n_centers"] == 4, r
