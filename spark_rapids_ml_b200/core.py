@@ -327,6 +327,12 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
             est = self.copy(params) if params else self
             return est._fit(dataset)
 
+        def fitMultiple(self, dataset: LocalDataFrame, paramMaps: Sequence[Dict[Any, Any]]) -> Iterator[Tuple[int, "_CumlModel"]]:
+            """pyspark.ml.Estimator.fitMultiple: (index, model) per param map, one fit each — what the reference falls back
+            to for KMeans (`_enable_fit_multiple_in_single_pass` is False there, core.py:1172-1228)."""
+            for index, pm in enumerate(paramMaps):
+                yield index, self.copy(pm)._fit(dataset)
+
     def _fit(self, dataset: LocalDataFrame) -> "_CumlModel":
         if self._use_cpu_fallback():
             # reference: core.py:1283-1295 falls back to pyspark.ml on CPU; this build has NO CPU path.
@@ -622,3 +628,8 @@ class _CumlModelWithPredictionCol(_CumlModelWithColumns):
     def setPredictionCol(self, value: str) -> "_CumlModelWithPredictionCol":
         self._set_params(predictionCol=value)
         return self
+
+    @property
+    def numFeatures(self) -> int:
+        """Number of features the model was trained on (reference core.py:1961-1967)."""
+        return int(self.n_cols) if self.n_cols is not None else -1

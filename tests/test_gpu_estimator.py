@@ -141,3 +141,19 @@ def test_session_confs_reach_the_fit(tmp_path):
         assert ko.max_center_rel_err(np.asarray(sorted(ref.tolist())), C) <= 1e-3      # a converged, sane model
     finally:
         LocalSession()
+
+
+def test_fit_multiple_and_num_features(session):
+    """pyspark.ml.Estimator.fitMultiple over param maps (one fit per map, as the reference does for KMeans) and
+    KMeansModel.numFeatures (reference core.py:1961-1967)."""
+    from spark_rapids_ml_b200.clustering import KMeans
+
+    X, _ = ko.make_blobs(300, 6, 3, seed=4)
+    df = session.createDataFrame([(r.tolist(),) for r in X], schema="features array<float>")
+    est = KMeans(k=2, num_workers=1, seed=1, initMode="random", maxIter=5)
+    maps = [{est.k: 2}, {est.k: 3, est.maxIter: 7}]
+    got = dict(est.fitMultiple(df, maps))
+    assert sorted(got) == [0, 1]
+    assert len(got[0].cluster_centers_) == 2 and len(got[1].cluster_centers_) == 3
+    assert got[1].getMaxIter() == 7 and got[0].getMaxIter() == 5 and est.getK() == 2      # the estimator itself is untouched
+    assert got[0].numFeatures == 6 and got[1].numFeatures == 6
