@@ -255,3 +255,21 @@ def test_assign_and_lloyd_beyond_256_clusters_run_in_chunks(n, d, k, gen):
         assert ko.compare_labels(X, C0, lg.cpu().numpy(), tau=TAU)["n_mismatch_outside_margin"] == 0
     finally:
         c.close()
+
+
+def test_baseline_cfg3_full_partition_every_row(ctx):
+    """BASELINE configs[2]'s per-GPU partition at its real size (k=256, d=256, 12.5 M rows): every row's label and min
+    distance against an fp64 PyTorch restatement on the device, one Lloyd step against the fp64 sums of those labels,
+    bitwise determinism — through the screening kernel and its fix-up."""
+    import torch
+    from _fullsize import check_every_row, check_one_step, make_blobs
+
+    X, C = make_blobs(12_500_000, 256, 256, seed=22)
+    r = check_every_row(ctx, X, C, chunk=250_000)
+    assert ctx.stats()["last_path"] == 2
+    assert r["outside_margin"] == 0, {k: v for k, v in r.items() if k != "labels"}
+    assert r["worst_mindist_rel_err"] <= 2e-4, r["worst_mindist_rel_err"]
+    rel, same = check_one_step(ctx, X, C, r["labels"])
+    assert rel <= 1e-5 and same, (rel, same)
+    del X
+    torch.cuda.empty_cache()

@@ -307,3 +307,20 @@ def test_baseline_config_shapes(ctx):
         if margin0.min() > 1e-5:
             assert ko.max_center_rel_err(one, C1) <= CENTER_RTOL
             assert ko.max_center_rel_err(Cg, ref["centers"]) <= 1e-3
+
+
+def test_baseline_cfg2_full_size_every_row(ctx):
+    """BASELINE configs[1] at its real size (k=64, n=10 M, d=128, one GPU): every row's label and min distance against an
+    fp64 PyTorch restatement on the device, one Lloyd step against the fp64 sums of those labels, bitwise determinism."""
+    import torch
+    from _fullsize import check_every_row, check_one_step, make_blobs
+
+    ctx.set_option("kernel_path", 2)
+    X, C = make_blobs(10_000_000, 128, 64, seed=21)
+    r = check_every_row(ctx, X, C)
+    assert r["outside_margin"] == 0, {k: v for k, v in r.items() if k != "labels"}
+    assert r["worst_mindist_rel_err"] <= 2e-4, r["worst_mindist_rel_err"]
+    rel, same = check_one_step(ctx, X, C, r["labels"])
+    assert rel <= 1e-5 and same, (rel, same)
+    del X
+    torch.cuda.empty_cache()
