@@ -666,35 +666,49 @@ std::vector<int64_t> sample_distinct(std::mt19937_64& rng, int64_t total, int m)
 // refinement that follows runs on the device (init_kmeans_parallel).
 void reduce_candidates(const std::vector<float>& D2, const std::vector<double>& wts, int M, int k, std::mt19937_64& rng,
                        std::vector<int64_t>* out) {
-  std::vector<double> d2(M), nd2(M), bestd2(M);
+  std::vector<double> d2(M), cum(M);
   std::vector<int> chosen;
   chosen.reserve(k);
-  auto pick = [&](const std::vector<double>& prob, double tot) {
+  // draw i with probability prob[i] / tot from the running sums cum[] (first i with u < cum[i])
+  auto pick = [&](double tot) {
     std::uniform_real_distribution<double> U(0.0, tot);
-    double u = U(rng), acc = 0;
-    for (int i = 0; i < M; ++i) { acc += prob[i]; if (u < acc) return i; }
-    return M - 1;
+    const double u = U(rng);
+    const int i = (int)(std::upper_bound(cum.begin(), cum.end(), u) - cum.begin());
+    return std::min(i, M - 1);
   };
-  std::vector<double> prob(M);
+  // potential of adding candidate c: sum_i w_i min(d2_i, D2[c][i]); four fixed partial sums (identical on every rank)
+  auto potential = [&](int c) {
+    const float* row = &D2[(size_t)c * M];
+    double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    int i = 0;
+    for (; i + 4 <= M; i += 4) {
+      p0 += wts[i] * std::min(d2[i], (double)row[i]);
+      p1 += wts[i + 1] * std::min(d2[i + 1], (double)row[i + 1]);
+      p2 += wts[i + 2] * std::min(d2[i + 2], (double)row[i + 2]);
+      p3 += wts[i + 3] * std::min(d2[i + 3], (double)row[i + 3]);
+    }
+    for (; i < M; ++i) p0 += wts[i] * std::min(d2[i], (double)row[i]);
+    return (p0 + p1) + (p2 + p3);
+  };
   double tot = 0;
-  for (int i = 0; i < M; ++i) { prob[i] = wts[i]; tot += prob[i]; }
-  int first = pick(prob, tot);
+  for (int i = 0; i < M; ++i) { tot += wts[i]; cum[i] = tot; }
+  const int first = pick(tot);
   chosen.push_back(first);
   for (int i = 0; i < M; ++i) d2[i] = (double)D2[(size_t)first * M + i];
   const int trials = 2 + (int)std::log((double)std::max(k, 2));
   for (int j = 1; j < k; ++j) {
     tot = 0;
-    for (int i = 0; i < M; ++i) { prob[i] = wts[i] * d2[i]; tot += prob[i]; }
+    for (int i = 0; i < M; ++i) { tot += wts[i] * d2[i]; cum[i] = tot; }
     double best_pot = -1;
     int best_c = 0;
     for (int tr = 0; tr < trials; ++tr) {
-      int c = tot > 0 ? pick(prob, tot) : (int)(rng() % M);
-      double pot = 0;
-      for (int i = 0; i < M; ++i) { nd2[i] = std::min(d2[i], (double)D2[(size_t)c * M + i]); pot += wts[i] * nd2[i]; }
-      if (best_pot < 0 || pot < best_pot) { best_pot = pot; best_c = c; bestd2 = nd2; }
+      const int c = tot > 0 ? pick(tot) : (int)(rng() % M);
+      const double pot = potential(c);
+      if (best_pot < 0 || pot < best_pot) { best_pot = pot; best_c = c; }
     }
     chosen.push_back(best_c);
-    d2 = bestd2;
+    const float* row = &D2[(size_t)best_c * M];
+    for (int i = 0; i < M; ++i) d2[i] = std::min(d2[i], (double)row[i]);
   }
   out->assign(chosen.begin(), chosen.end());
 }
