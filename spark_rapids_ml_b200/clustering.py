@@ -278,15 +278,8 @@ class KMeansModel(KMeansClass, _CumlModelWithPredictionCol, _KMeansCumlParams):
         def _construct_kmeans(gpu: int = 0) -> Any:
             return _DeviceKMeans(gpu)
 
-        def _transform_internal(kmeans: Any, df: Union[pd.DataFrame, np.ndarray]) -> pd.Series:
-            import torch
-
-            from .utils import DeviceRowAppender
-
+        def _append_features(app: Any, df: Union[pd.DataFrame, np.ndarray]) -> None:
             n_b = len(df)
-            if n_b == 0:
-                return pd.Series([], dtype="int32")
-            app = DeviceRowAppender(kmeans.ctx, n_cols, first_capacity=n_b)
             if isinstance(df, pd.DataFrame) and alias.data in df.columns:
                 col = df[alias.data]
                 bufs = arrow_list_column_buffers(col, n_cols)
@@ -308,8 +301,34 @@ class KMeansModel(KMeansClass, _CumlModelWithPredictionCol, _KMeansCumlParams):
                 if arr.ndim != 2 or arr.shape[1] != n_cols:
                     raise ValueError(f"feature rows do not match the model's {n_cols} columns")
                 app.append_values(arr.reshape(-1), None, n_b)
+
+        def _transform_many(kmeans: Any, dfs: List[Union[pd.DataFrame, np.ndarray]]) -> List[pd.Series]:
+            """Several input batches in ONE device pass: every batch is ingested into the same device matrix, one
+            b2k_kmeans_assign labels all rows, one read-back, one Series per input batch (same order, same lengths).
+            The per-batch host overhead (allocation, launches, a synchronising read-back) is what a 10 000-row Arrow batch
+            costs most; core._iter_transform groups batches up to ~1 M rows."""
+            from .utils import DeviceRowAppender
+
+            sizes = [len(df) for df in dfs]
+            total = sum(sizes)
+            if total == 0:
+                return [pd.Series([], dtype="int32") for _ in dfs]
+            app = DeviceRowAppender(kmeans.ctx, n_cols, first_capacity=total)
+            for df, n_b in zip(dfs, sizes):
+                if n_b:
+                    _append_features(app, df)
             X = app.finish()
             labels, _ = kmeans.ctx.kmeans_assign(X, kmeans.C)
-            return pd.Series(labels.cpu().numpy())
+            host = labels.cpu().numpy()
+            out, o = [], 0
+            for n_b in sizes:
+                out.append(pd.Series(host[o:o + n_b]))
+                o += n_b
+            return out
 
+        def _transform_internal(kmeans: Any, df: Union[pd.DataFrame, np.ndarray]) -> pd.Series:
+            return _transform_many(kmeans, [df])[0]
+
+        _transform_internal.many = _transform_many  # type: ignore[attr-defined]
+        _transform_internal.row_bytes = 4 * int(n_cols or 1)  # type: ignore[attr-defined]
         return _construct_kmeans, _transform_internal, None

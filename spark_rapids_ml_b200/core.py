@@ -364,6 +364,33 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
         return cls.read().load(path)
 
 
+TRANSFORM_GROUP_ROWS = 1 << 20    # rows labelled per device pass when the transform function can take several batches ...
+TRANSFORM_GROUP_BYTES = 2 << 30   # ... and the cap on the device matrix they form (transform function's `row_bytes`)
+
+
+def _iter_transform(transform_internal: Callable, get_model: Callable[[], Any], frames: Iterator[Any]) -> Iterator[Any]:
+    """One result per input frame, in order.  When the model's transform function offers `.many` (KMeans), consecutive
+    frames are grouped up to TRANSFORM_GROUP_ROWS rows and labelled in one device pass; otherwise frame by frame, as the
+    reference does (core.py:1900-1915)."""
+    many = getattr(transform_internal, "many", None)
+    if many is None:
+        for f in frames:
+            yield transform_internal(get_model(), f)
+        return
+    row_bytes = max(1, int(getattr(transform_internal, "row_bytes", 1)))
+    limit = max(1, min(TRANSFORM_GROUP_ROWS, TRANSFORM_GROUP_BYTES // row_bytes))
+    group: List[Any] = []
+    rows = 0
+    for f in frames:
+        group.append(f)
+        rows += len(f)
+        if rows >= limit:
+            yield from many(get_model(), group)
+            group, rows = [], 0
+    if group:
+        yield from many(get_model(), group)
+
+
 def _parse_conf_bool(v: str) -> bool:
     if v not in ("true", "false"):
         raise ValueError(v)
@@ -603,19 +630,19 @@ class _CumlModelWithColumns(_CumlModel):
         out_parts: List[List[pa.Array]] = []
         state: Dict[str, Any] = {}
         for pid, part in enumerate(dataset._parts):
-            arrs: List[pa.Array] = []
-            for batch in part:
-                if "model" not in state:
-                    gpu = _CumlCommon._set_gpu_device(BarrierTaskContext(pid, len(dataset._parts)), True, True)
-                    state["model"] = construct(gpu)
-                pdf = batch.to_pandas(types_mapper=pd.ArrowDtype) if dataset.arrow_backed_pandas else batch.to_pandas()
-                if input_cols:
-                    feats: Any = pdf[input_cols]
-                else:
-                    feats = pdf[[input_col]].rename(columns={input_col: alias.data})
-                res = transform_internal(state["model"], feats)
-                arrs.append(pa.array(np.asarray(res), type=pa.int32()))
-            out_parts.append(arrs)
+            def frames(part: Any = part, pid: int = pid) -> Iterator[Any]:
+                for batch in part:
+                    if "model" not in state:
+                        gpu = _CumlCommon._set_gpu_device(BarrierTaskContext(pid, len(dataset._parts)), True, True)
+                        state["model"] = construct(gpu)
+                    pdf = batch.to_pandas(types_mapper=pd.ArrowDtype) if dataset.arrow_backed_pandas else batch.to_pandas()
+                    if input_cols:
+                        yield pdf[input_cols]
+                    else:
+                        yield pdf[[input_col]].rename(columns={input_col: alias.data})
+
+            out_parts.append([pa.array(np.asarray(res), type=pa.int32())
+                              for res in _iter_transform(transform_internal, lambda: state["model"], frames())])
         if "model" in state and hasattr(state["model"], "close"):
             state["model"].close()
         assert n_cols is None or n_cols > 0

@@ -114,8 +114,9 @@ def transform_with_pandas_udf(model: Any, dataset: Any, data_alias: str, set_gpu
         gpu = set_gpu(TaskContext.get(), local)
         device_model = construct(gpu)
         try:
-            for pdf in iterator:
-                yield transform_internal(device_model, pdf)
+            from .core import _iter_transform   # groups consecutive batches into one device pass where possible
+
+            yield from _iter_transform(transform_internal, lambda: device_model, iterator)
         finally:
             if hasattr(device_model, "close"):
                 device_model.close()
