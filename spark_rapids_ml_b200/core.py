@@ -631,15 +631,19 @@ class _CumlModelWithColumns(_CumlModel):
         state: Dict[str, Any] = {}
         for pid, part in enumerate(dataset._parts):
             def frames(part: Any = part, pid: int = pid) -> Iterator[Any]:
-                for batch in part:
-                    if "model" not in state:
-                        gpu = _CumlCommon._set_gpu_device(BarrierTaskContext(pid, len(dataset._parts)), True, True)
-                        state["model"] = construct(gpu)
-                    pdf = batch.to_pandas(types_mapper=pd.ArrowDtype) if dataset.arrow_backed_pandas else batch.to_pandas()
-                    if input_cols:
-                        yield pdf[input_cols]
-                    else:
-                        yield pdf[[input_col]].rename(columns={input_col: alias.data})
+                from .sparkshim.sql import _batches_to_pdf_iter
+
+                def selected() -> Iterator[pa.RecordBatch]:   # feature columns only, renamed at the Arrow level (zero-copy)
+                    for batch in part:
+                        if "model" not in state:
+                            gpu = _CumlCommon._set_gpu_device(BarrierTaskContext(pid, len(dataset._parts)), True, True)
+                            state["model"] = construct(gpu)
+                        if input_cols:
+                            yield batch.select(list(input_cols))
+                        else:
+                            yield batch.select([input_col]).rename_columns([alias.data])
+
+                return _batches_to_pdf_iter(selected(), dataset.arrow_backed_pandas)
 
             out_parts.append([pa.array(np.asarray(res), type=pa.int32())
                               for res in _iter_transform(transform_internal, lambda: state["model"], frames())])
