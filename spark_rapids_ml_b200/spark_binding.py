@@ -79,7 +79,66 @@ def run_barrier_fit(df: Any, train_udf: Callable[[Iterator[pd.DataFrame]], Itera
     if df.rdd.getNumPartitions() != num_workers:
         df = df.repartition(num_workers)
     pipelined_rdd = df.mapInPandas(train_udf, schema=out_schema).rdd.barrier().mapPartitions(lambda x: x)
+    pipelined_rdd = try_stage_level_scheduling(pipelined_rdd, df)
     return pipelined_rdd.collect()
+
+
+def _version_tuple(v: str) -> Tuple[int, ...]:
+    out = []
+    for part in str(v).split(".")[:3]:
+        digits = "".join(ch for ch in part if ch.isdigit())
+        out.append(int(digits) if digits else 0)
+    return tuple(out + [0] * (3 - len(out)))
+
+
+def stage_level_scheduling_plan(spark_version: str, conf_get: Callable[[str], Optional[str]], is_local_mode: bool,
+                                plugins: str = "", rapids_sql_enabled: str = "true") -> Tuple[Optional[Tuple[int, float]], str]:
+    """Decide whether the training stage gets its own task resource profile (reference core.py:637-740): so that each
+    barrier task lands on a different executor and owns its GPU while ETL stages keep their fractional GPU amounts.
+    -> ((task_cpus, task_gpus) or None, reason).  Pure function of the Spark version and confs: unit-tested without Spark."""
+    if is_local_mode:
+        return None, "local mode: the partition id selects the GPU"
+    ver = _version_tuple(spark_version)
+    if ver < (3, 4, 0):
+        return None, "stage-level scheduling requires Spark 3.4.0+"
+    master = conf_get("spark.master") or ""
+    if ver < (3, 5, 1) and not (master.startswith("spark://") or master.startswith("local-cluster")):
+        return None, "Spark %s: stage-level scheduling requires standalone or local-cluster mode" % spark_version
+    cores, gpus = conf_get("spark.executor.cores"), conf_get("spark.executor.resource.gpu.amount")
+    if cores is None or gpus is None:
+        return None, "spark.executor.cores and spark.executor.resource.gpu.amount must be set"
+    if int(cores) == 1:
+        return None, "spark.executor.cores = 1: one task at a time anyway"
+    if int(float(gpus)) > 1:
+        return None, "spark.executor.resource.gpu.amount > 1: left to the user's configuration"
+    task_gpu = conf_get("spark.task.resource.gpu.amount")
+    if task_gpu is not None and float(task_gpu) == float(gpus):
+        return None, "spark.task.resource.gpu.amount equals the executor's: already one task per GPU"
+    # more than half of the executor's cores => two training tasks never share an executor; with the RAPIDS SQL plugin
+    # active the training task takes the whole executor so that no ETL task runs beside it
+    sql_plugin = "com.nvidia.spark.SQLPlugin" in (plugins or "") and str(rapids_sql_enabled).lower() == "true"
+    task_cpus = int(cores) if sql_plugin else int(cores) // 2 + 1
+    return (task_cpus, 1.0), "training tasks require cores=%d, gpu=1.0" % task_cpus
+
+
+def try_stage_level_scheduling(rdd: Any, dataset: Any) -> Any:
+    """rdd.withResources(profile) when stage_level_scheduling_plan says so; any surprise leaves the RDD as it is."""
+    try:
+        session = dataset.sparkSession
+        sc = session.sparkContext
+        sconf = sc.getConf()
+        plan, _ = stage_level_scheduling_plan(str(session.version), lambda k: sconf.get(k), is_local(dataset),
+                                              session.conf.get("spark.plugins", " "),
+                                              session.conf.get("spark.rapids.sql.enabled", "true"))
+        if plan is None:
+            return rdd
+        from pyspark.resource.profile import ResourceProfileBuilder
+        from pyspark.resource.requests import TaskResourceRequests
+
+        treqs = TaskResourceRequests().cpus(plan[0]).resource("gpu", plan[1])
+        return rdd.withResources(ResourceProfileBuilder().require(treqs).build)
+    except Exception:
+        return rdd
 
 
 def current_barrier_context() -> Any:

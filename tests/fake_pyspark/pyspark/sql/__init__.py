@@ -28,12 +28,31 @@ def _to_spark_type(t):
             pa.string(): StringType()}.get(t, StringType())
 
 
+CLUSTER_CONF = None   # a dict of Spark confs makes the fake session look like a cluster (tests of stage-level scheduling)
+
+
+class _Conf:
+    def get(self, key, default=None):
+        return (CLUSTER_CONF or {}).get(key, default)
+
+
 class _SC:
-    master = "local[1]"
+    @property
+    def master(self):
+        return (CLUSTER_CONF or {}).get("spark.master", "local[1]")
+
+    def getConf(self):
+        return _Conf()
 
 
 class SparkSession:
     sparkContext = _SC()
+    version = "3.5.1"
+    conf = _Conf()
+
+    @classmethod
+    def getActiveSession(cls):
+        return None
 
 
 class RDD:
@@ -49,6 +68,10 @@ class RDD:
 
     def mapPartitions(self, f):
         CALLS.append(("rdd.mapPartitions", None))
+        return self
+
+    def withResources(self, profile):
+        CALLS.append(("rdd.withResources", profile))
         return self
 
     def collect(self):

@@ -132,3 +132,36 @@ def test_constructor_defaults_from_session_confs():
         assert "float32_inputs" not in KMeans()._input_kwargs                     # nothing set: nothing injected
     finally:
         LS._active = saved
+
+
+def test_stage_level_scheduling_plan():
+    """reference core.py:637-740 (_skip_stage_level_scheduling / _try_stage_level_scheduling) as a pure decision function."""
+    from spark_rapids_ml_b200.spark_binding import stage_level_scheduling_plan as plan
+
+    base = {"spark.master": "spark://h:7077", "spark.executor.cores": "12", "spark.executor.resource.gpu.amount": "1",
+            "spark.task.resource.gpu.amount": "0.08"}
+
+    def p(version="3.5.1", local=False, plugins="", sql="true", **over):
+        conf = dict(base)
+        for k, v in over.items():
+            key = k.replace("__", ".")
+            if v is None:
+                conf.pop(key, None)
+            else:
+                conf[key] = v
+        return plan(version, conf.get, local, plugins, sql)[0]
+
+    assert p() == (7, 1.0)                                              # cores // 2 + 1: two tasks never share an executor
+    assert p(plugins="com.nvidia.spark.SQLPlugin") == (12, 1.0)         # SQL plugin on: the whole executor
+    assert p(plugins="com.nvidia.spark.SQLPlugin", sql="false") == (7, 1.0)
+    assert p(spark__task__resource__gpu__amount=None) == (7, 1.0)       # ETL tasks take no GPU: training still must
+    assert p(local=True) is None
+    assert p(version="3.3.2") is None
+    assert p(version="3.4.1", spark__master="yarn") is None             # 3.4.x: standalone / local-cluster only
+    assert p(version="3.4.1") == (7, 1.0)
+    assert p(version="3.5.1", spark__master="yarn") == (7, 1.0)
+    assert p(version="3.10.0", spark__master="yarn") == (7, 1.0)        # numeric, not lexicographic, version order
+    assert p(spark__executor__cores=None) is None and p(spark__executor__resource__gpu__amount=None) is None
+    assert p(spark__executor__cores="1") is None
+    assert p(spark__executor__resource__gpu__amount="2") is None
+    assert p(spark__task__resource__gpu__amount="1") is None            # already one task per GPU

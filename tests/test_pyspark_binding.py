@@ -261,3 +261,27 @@ def test_barrier_rdd_chain_error_is_retried_after_repartition():
     first_collect = c.index("rdd.collect")
     assert "repartition" in c[first_collect:] and "repartition" not in c[:first_collect], r
     assert r["warned"] and r["n_centers"] == 4, r
+
+
+_STAGE = '''
+import pyspark.sql as ps
+ps.CLUSTER_CONF = {"spark.master": "spark://head:7077", "spark.executor.cores": "8",
+                   "spark.executor.resource.gpu.amount": "1", "spark.task.resource.gpu.amount": "0.125"}
+local = sess.from_numpy(X.astype(np.float32), col="features", num_partitions=1)
+del CALLS[:]
+# a cluster master: the GPU comes from the task's resources, as under a real scheduler
+import pyspark
+pyspark.TaskContext.resources = lambda self: {"gpu": type("R", (), {"addresses": ["0"]})()}
+model = KMeans(k=4, maxIter=5, initMode="random", seed=1, num_workers=1).setFeaturesCol("features").fit(DataFrame(local))
+calls = [(c[0], c[1]) for c in CALLS if c[0] in ("rdd.barrier", "rdd.mapPartitions", "rdd.withResources", "rdd.collect")]
+print("RESULT " + json.dumps({"calls": calls, "n_centers": len(model.cluster_centers_)}))
+'''
+
+
+def test_training_stage_gets_its_own_resource_profile_on_a_cluster():
+    """reference core.py:693-740: on a standalone cluster the barrier stage is submitted with a task resource profile
+    (more than half of the executor's cores + one GPU) between mapPartitions and collect."""
+    r = _run(_COMMON + _CPU_STUBS + _STAGE)
+    names = [c[0] for c in r["calls"]]
+    assert names == ["rdd.barrier", "rdd.mapPartitions", "rdd.withResources", "rdd.collect"], r
+    assert r["calls"][2][1] == {"cpus": 5, "gpu": 1.0} and r["n_centers"] == 4, r
