@@ -223,6 +223,38 @@ class KMeans(KMeansClass, _CumlEstimator, _KMeansCumlParams):
         return [_one_model_row([r]) for r in rows]
 
 
+_TRANSFORM_CONTEXTS: Dict[int, Any] = {}
+_TRANSFORM_CONTEXTS_LOCK = __import__("threading").Lock()
+
+
+def _transform_context(gpu: int) -> Any:
+    """One library context per (process, GPU) for transform tasks: a Spark Python worker is reused across tasks, and a
+    context's set-up (stream, pinned staging buffers, scratch, copy threads) costs more than labelling a small
+    partition.  Released at interpreter exit."""
+    from . import _native
+
+    with _TRANSFORM_CONTEXTS_LOCK:
+        ctx = _TRANSFORM_CONTEXTS.get(gpu)
+        if ctx is None:
+            ctx = _native.Context(gpu)
+            _TRANSFORM_CONTEXTS[gpu] = ctx
+            if len(_TRANSFORM_CONTEXTS) == 1:
+                import atexit
+
+                atexit.register(_close_transform_contexts)
+        return ctx
+
+
+def _close_transform_contexts() -> None:
+    with _TRANSFORM_CONTEXTS_LOCK:
+        for ctx in _TRANSFORM_CONTEXTS.values():
+            try:
+                ctx.close()
+            except Exception:
+                pass
+        _TRANSFORM_CONTEXTS.clear()
+
+
 class KMeansModel(KMeansClass, _CumlModelWithPredictionCol, _KMeansCumlParams):
     """reference: clustering.py:505-604."""
 
@@ -267,13 +299,11 @@ class KMeansModel(KMeansClass, _CumlModelWithPredictionCol, _KMeansCumlParams):
             def __init__(self, gpu: int) -> None:
                 import torch
 
-                from . import _native
-
-                self.ctx = _native.Context(gpu)
+                self.ctx = _transform_context(gpu)
                 self.C = torch.tensor(cluster_centers_, dtype=torch.float32, device=self.ctx.device)
 
-            def close(self) -> None:
-                self.ctx.close()
+            def close(self) -> None:   # the context (pinned staging, scratch, copy threads) stays with the process
+                self.C = None
 
         def _construct_kmeans(gpu: int = 0) -> Any:
             return _DeviceKMeans(gpu)
