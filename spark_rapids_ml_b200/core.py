@@ -340,7 +340,9 @@ class _CumlEstimator(EstimatorBase, _CumlCaller):
         return self._fit_internal(dataset, None)[0]
 
     # -- persistence (core.py:268-307): Spark's DefaultParamsWriter layout (path/metadata/part-00000 JSON) --
-    def save(self, path: str, overwrite: bool = True) -> None:
+    def save(self, path: str, overwrite: bool = False) -> None:
+        """pyspark.ml.util.MLWritable.save: a shortcut of write().save(path) — an existing path is an error unless
+        write().overwrite() (or overwrite=True here) is used."""
         w = self.write()
         (w.overwrite() if overwrite else w).save(path)
 
@@ -584,7 +586,9 @@ class _CumlModel(ModelBase, _CumlParams, _CumlCommon):
         raise NotImplementedError
 
     # -- persistence (core.py:310-355): metadata as the estimator + path/data = json.dumps(model attributes) --
-    def save(self, path: str, overwrite: bool = True) -> None:
+    def save(self, path: str, overwrite: bool = False) -> None:
+        """pyspark.ml.util.MLWritable.save: a shortcut of write().save(path) — an existing path is an error unless
+        write().overwrite() (or overwrite=True here) is used."""
         w = self.write()
         (w.overwrite() if overwrite else w).save(path)
 

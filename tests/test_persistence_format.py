@@ -85,3 +85,22 @@ def test_directories_written_by_the_reference_load_here(tmp_path):
     meta = json.loads(open(os.path.join(back, "metadata", "part-00000")).read())
     assert meta["uid"] == model.uid and meta["paramMap"]["featuresCol"] == "feats" and meta["_num_workers"] == 4
     assert json.loads(open(os.path.join(back, "data", "part-00000")).read())["cluster_centers_"] == centers
+
+
+def test_save_is_write_save_and_refuses_an_existing_path(tmp_path):
+    """pyspark.ml.util.MLWritable.save(path) == write().save(path): no silent overwrite (reference tests use
+    estimator.save(path) / Model.load(path), tests/test_kmeans.py:505-512)."""
+    km = KMeans(k=2)
+    p = str(tmp_path / "kmeans")
+    km.save(p)
+    assert KMeans.load(p).getK() == 2
+    with pytest.raises(IOError):
+        km.save(p)
+    km.write().overwrite().save(p)
+    m = KMeansModel(cluster_centers_=[[0.5, 0.5], [8.5, 8.5]], n_cols=2, dtype="float32")
+    mp = str(tmp_path / "kmeans_model")
+    m.save(mp)
+    m2 = KMeansModel.load(mp)
+    assert m2.hasSummary is False and all(np.array_equal(a, b) for a, b in zip(m.clusterCenters(), m2.clusterCenters()))
+    with pytest.raises(IOError):
+        m.save(mp)
