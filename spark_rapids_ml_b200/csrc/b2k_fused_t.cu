@@ -28,7 +28,7 @@
 //
 // Replaces (for these shapes) cuML's fusedL2NN + reduce_rows_by_key reached from
 // spark_rapids_ml/clustering.py:412-415.  Algorithmic HBM bytes per launch: 4*n*d (X once)
-// + 8*n (row norms) [+ 4*n labels / 4*n mindist when requested] + 75 * (k*d + k) * 4 partials + 40 B per deferred row.
+// + 8*n (row norms) [+ 4*n labels / 4*n mindist when requested] + 78 * (k*d + k) * 4 partials (74 CTA pairs + 4 fix-up slots) + 40 B per deferred row.
 #include <float.h>
 #include <stdio.h>
 
